@@ -1,0 +1,592 @@
+// elementwise.cu -- the HBM-bound kernels of the SGA iteration: Gumbel soft rounding fused with the two
+// entropy-model rate terms, the distortion/PSNR reduction, the IGDN point-wise pieces of the fp32 path and
+// the Adam update.  Coalesced (pairs of adjacent channels per thread, one Philox call per pair), warp-shuffle
+// + one atomicAdd(double) per warp for the per-image reductions.
+//
+// Reference arithmetic restated here (file:line into /root/reference):
+//   soft round        sga.py:88-98, 111-121 (+ tfp RelaxedOneHotCategorical.sample)
+//   factorised prior  tfc EntropyBottleneck._likelihood, sga.py:100-104; learned_prior.py:78-121, 296-347
+//   Gaussian box      tfc GaussianConditional._likelihood, sga.py:129-136; utils.py:80-102
+//   lower_bound grad  math_ops.py:63-76
+//   bpp / mse / psnr  sga.py:143-154, 167-174
+//   Adam              adam.py:36-57
+#include "common.cuh"
+#include "philox.cuh"
+#include "kernels.h"
+
+namespace sga {
+
+// ------------------------------------------------------------------------------------------------
+// soft round of one element. Returns v_tilde, writes d v_tilde / d v.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float soft_round_one(float v, float u0, float u1, float T, float eps, float* dvt) {
+  const float f = floorf(v), c = ceilf(v);
+  const float lo = -1.0f + eps, hi = 1.0f - eps;
+  const float d = v - f, e = c - v;
+  const float dc = fminf(fmaxf(d, lo), hi), ec = fminf(fmaxf(e, lo), hi);
+  const float l0 = -atanhf(dc) / T, l1 = -atanhf(ec) / T;
+  const float g0 = -logf(-logf(u0)), g1 = -logf(-logf(u1));
+  const float a = ((l1 + g1) - (l0 + g0)) / T;
+  const float s1 = 1.0f / (1.0f + expf(-a));
+  const float s0 = 1.0f - s1;
+  const float p0 = (d >= lo && d <= hi) ? 1.0f : 0.0f;
+  const float p1 = (e >= lo && e <= hi) ? 1.0f : 0.0f;
+  const float dl0 = -p0 / ((1.0f - dc * dc) * T);
+  const float dl1 = p1 / ((1.0f - ec * ec) * T);
+  *dvt = (c - f) * s1 * s0 * (dl1 - dl0) / T;
+  return f * s0 + c * s1;
+}
+
+__device__ __forceinline__ void pair_uniforms(const float* __restrict__ inj, long long numel, long long e0,
+                                              uint64_t seed, int step, int tensor_id, float u[4]) {
+  if (inj != nullptr) {  // injected: [2][numel], DOWN logits first
+    u[0] = inj[e0];
+    u[1] = inj[numel + e0];
+    const bool has2 = (e0 + 1 < numel);
+    u[2] = has2 ? inj[e0 + 1] : 0.5f;
+    u[3] = has2 ? inj[numel + e0 + 1] : 0.5f;
+  } else {
+    const Philox4 r = philox4x32_10(static_cast<uint32_t>(e0 >> 1), static_cast<uint32_t>(step),
+                                    static_cast<uint32_t>(tensor_id), 0u, static_cast<uint32_t>(seed),
+                                    static_cast<uint32_t>(seed >> 32));
+    u[0] = bits_to_uniform(r.x);
+    u[1] = bits_to_uniform(r.y);
+    u[2] = bits_to_uniform(r.z);
+    u[3] = bits_to_uniform(r.w);
+  }
+}
+
+__global__ void k_soft_round(const float* __restrict__ v, const float* __restrict__ inj, long long numel, float T,
+                             float eps, uint64_t seed, int step, int tensor_id, float* __restrict__ vt,
+                             float* __restrict__ dvt) {
+  const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long e0 = pair * 2;
+  if (e0 >= numel) return;
+  float u[4];
+  pair_uniforms(inj, numel, e0, seed, step, tensor_id, u);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (e0 + k < numel) {
+      float d;
+      const float r = soft_round_one(v[e0 + k], u[2 * k], u[2 * k + 1], T, eps, &d);
+      vt[e0 + k] = r;
+      if (dvt) dvt[e0 + k] = d;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// factorised prior: per-channel 1->3->3->3->1 network evaluated in forward mode (value and slope).
+// Packed parameters pk[j*C + c], j in [0,44): softplus(matrix) and tanh(factor) are precomputed at bind time.
+//   0..2 M0 | 3..5 B0 | 6..8 F0 | 9..17 M1 (r*3+k) | 18..20 B1 | 21..23 F1 | 24..32 M2 | 33..35 B2 | 36..38 F2
+//   39..41 M3 | 42 B3 | 43 pad
+// ------------------------------------------------------------------------------------------------
+struct EbParams { float p[44]; };
+
+__device__ __forceinline__ void eb_load(const float* __restrict__ pk, int C, int c, EbParams& P) {
+#pragma unroll
+  for (int j = 0; j < 43; ++j) P.p[j] = __ldg(pk + j * C + c);
+}
+
+__device__ __forceinline__ void eb_logit(const EbParams& P, float u, float* L, float* dL) {
+  float h[3], d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    h[r] = P.p[r] * u + P.p[3 + r];
+    d[r] = P.p[r];
+    const float t = tanhf(h[r]);
+    h[r] += P.p[6 + r] * t;
+    d[r] *= 1.0f + P.p[6 + r] * (1.0f - t * t);
+  }
+#pragma unroll
+  for (int layer = 0; layer < 2; ++layer) {
+    const int mo = 9 + 15 * layer, bo = 18 + 15 * layer, fo = 21 + 15 * layer;
+    float h2[3], d2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float a = P.p[bo + r], g = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a += P.p[mo + r * 3 + k] * h[k];
+        g += P.p[mo + r * 3 + k] * d[k];
+      }
+      const float t = tanhf(a);
+      h2[r] = a + P.p[fo + r] * t;
+      d2[r] = g * (1.0f + P.p[fo + r] * (1.0f - t * t));
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { h[r] = h2[r]; d[r] = d2[r]; }
+  }
+  float a = P.p[42], g = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { a += P.p[39 + k] * h[k]; g += P.p[39 + k] * d[k]; }
+  *L = a;
+  *dL = g;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float signf_(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
+
+// p = |sigmoid(s*upper) - sigmoid(s*lower)|, s = -sign(lower+upper) (stop-gradient)
+__device__ __forceinline__ float eb_likelihood_one(const EbParams& P, float zt, float* dp) {
+  float lower, dlower, upper, dupper;
+  eb_logit(P, zt - 0.5f, &lower, &dlower);
+  eb_logit(P, zt + 0.5f, &upper, &dupper);
+  const float s = -signf_(lower + upper);
+  const float su = sigmoidf_(s * upper), sl = sigmoidf_(s * lower);
+  const float diff = su - sl;
+  *dp = signf_(diff) * s * (su * (1.0f - su) * dupper - sl * (1.0f - sl) * dlower);
+  return fabsf(diff);
+}
+
+__global__ void k_eb_likelihood(const float* __restrict__ zt, long long numel, int C, const float* __restrict__ pk,
+                                float* __restrict__ p_out, float* __restrict__ dp_out) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= numel) return;
+  EbParams P;
+  eb_load(pk, C, static_cast<int>(e % C), P);
+  float dp;
+  const float p = eb_likelihood_one(P, zt[e], &dp);
+  if (p_out) p_out[e] = p;
+  if (dp_out) dp_out[e] = dp;
+}
+
+__global__ void k_eb_pack(const float* m0, const float* m1, const float* m2, const float* m3, const float* b0,
+                          const float* b1, const float* b2, const float* b3, const float* f0, const float* f1,
+                          const float* f2, int C, float* __restrict__ pk) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  auto sp = [](float x) { return (x > 20.0f) ? x : log1pf(expf(x)); };
+  for (int r = 0; r < 3; ++r) {
+    pk[(0 + r) * C + c] = sp(m0[c * 3 + r]);
+    pk[(3 + r) * C + c] = b0[c * 3 + r];
+    pk[(6 + r) * C + c] = tanhf(f0[c * 3 + r]);
+    pk[(18 + r) * C + c] = b1[c * 3 + r];
+    pk[(21 + r) * C + c] = tanhf(f1[c * 3 + r]);
+    pk[(33 + r) * C + c] = b2[c * 3 + r];
+    pk[(36 + r) * C + c] = tanhf(f2[c * 3 + r]);
+    pk[(39 + r) * C + c] = sp(m3[c * 3 + r]);
+    for (int k = 0; k < 3; ++k) {
+      pk[(9 + r * 3 + k) * C + c] = sp(m1[c * 9 + r * 3 + k]);
+      pk[(24 + r * 3 + k) * C + c] = sp(m2[c * 9 + r * 3 + k]);
+    }
+  }
+  pk[42 * C + c] = b3[c];
+  pk[43 * C + c] = 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1(z)+K2: soft round of z fused with the factorised-prior rate.
+//   zt_act : z_tilde in the activation dtype (input of h_s)       g_rate: d(rate)/d z_tilde (fp32)
+//   dz     : d z_tilde / d z                                      bits[n] += -ln p  (double)
+// hard != 0: z_tilde = rint(z) (sga.py:240-241), no noise.
+// ------------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ inj, long long numel,
+                         long long per_image, int C, const float* __restrict__ pk, float T, float eps, uint64_t seed,
+                         int step, int hard, float rate_scale, AT* __restrict__ zt_act, float* __restrict__ g_rate,
+                         float* __restrict__ dz, double* __restrict__ bits) {
+  const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long e0 = pair * 2;
+  float nll = 0.0f;
+  long long img = -1;
+  if (e0 < numel) {
+    img = e0 / per_image;
+    float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Z, u);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long e = e0 + k;
+      if (e < numel) {
+        float d = 0.0f, zt;
+        if (hard) zt = rintf(z[e]);
+        else zt = soft_round_one(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
+        EbParams P;
+        eb_load(pk, C, static_cast<int>(e % C), P);
+        float dp;
+        const float p = eb_likelihood_one(P, zt, &dp);
+        const float pc = fmaxf(p, 1e-9f);
+        nll += -logf(pc);
+        zt_act[e] = from_f32<AT>(zt);
+        if (g_rate) g_rate[e] = (-rate_scale / pc) * dp;
+        if (dz) dz[e] = d;
+      }
+    }
+  }
+  // per-image reduction: a warp may straddle an image boundary only if per_image is not a multiple of 64
+  const unsigned full = 0xffffffffu;
+  const long long img0 = __shfl_sync(full, img, 0);
+  const bool uniform = __all_sync(full, img == img0);
+  if (uniform) {
+    const float s = warp_sum(nll);
+    if ((threadIdx.x & 31) == 0 && img0 >= 0) atomicAdd(bits + img0, static_cast<double>(s));
+  } else if (img >= 0) {
+    atomicAdd(bits + img, static_cast<double>(nll));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1(y)+K4: soft round of y fused with the Gaussian-conditional rate.  Iterates over the pixel grid of
+// h2 = h_s(z_tilde) [N,Hh,Wh,2C]; pixels outside y's grid (the crop of sga.py:126-128) get zero gradient.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float std_cdf(float x) { return 0.5f * erfcf(-0.70710678118654752440f * x); }
+
+__device__ __forceinline__ float gauss_likelihood_one(float yt, float mu, float logsigma, float* dp_dy, float* dp_dsb,
+                                                      float* sigma_out) {
+  const float sigma = expf(logsigma);
+  const float sb = fmaxf(sigma, 0.11f);
+  const float d = yt - mu;
+  const float v = fabsf(d);
+  const float a = (0.5f - v) / sb, b = (-0.5f - v) / sb;
+  const float p = std_cdf(a) - std_cdf(b);
+  const float k = 0.39894228040143267794f;
+  const float pa = expf(-0.5f * a * a) * k, pb = expf(-0.5f * b * b) * k;
+  *dp_dy = -signf_(d) * (pa - pb) / sb;
+  *dp_dsb = -(a * pa - b * pb) / sb;
+  *sigma_out = sigma;
+  return p;
+}
+
+__global__ void k_gauss_likelihood(const float* __restrict__ yt, const float* __restrict__ mu,
+                                   const float* __restrict__ ls, long long numel, float* __restrict__ p_out,
+                                   float* __restrict__ dpdy, float* __restrict__ dpdsb) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= numel) return;
+  float a, b, s;
+  const float p = gauss_likelihood_one(yt[e], mu[e], ls[e], &a, &b, &s);
+  if (p_out) p_out[e] = p;
+  if (dpdy) dpdy[e] = a;
+  if (dpdsb) dpdsb[e] = b;
+}
+
+template <typename AT>
+__global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ inj, const float* __restrict__ h2,
+                         int N, int Hy, int Wy, int Hh, int Wh, int C, float T, float eps, uint64_t seed, int step,
+                         int hard, float rate_scale, AT* __restrict__ yt_act, float* __restrict__ g_rate,
+                         float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits) {
+  const int halfC = C >> 1;
+  const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long npairs = static_cast<long long>(N) * Hh * Wh * halfC;
+  float nll = 0.0f;
+  long long img = -1;
+  if (pair < npairs) {
+    const int cp = static_cast<int>(pair % halfC);
+    long long pix = pair / halfC;
+    const int j = static_cast<int>(pix % Wh);
+    pix /= Wh;
+    const int i = static_cast<int>(pix % Hh);
+    const int n = static_cast<int>(pix / Hh);
+    const long long hpix = (static_cast<long long>(n) * Hh + i) * Wh + j;
+    const int c = cp * 2;
+    if (i < Hy && j < Wy) {
+      img = n;
+      const long long numel = static_cast<long long>(N) * Hy * Wy * C;
+      const long long e0 = ((static_cast<long long>(n) * Hy + i) * Wy + j) * C + c;
+      float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+      if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long long e = e0 + k;
+        float d = 0.0f, yt;
+        if (hard) yt = rintf(y[e]);
+        else yt = soft_round_one(y[e], u[2 * k], u[2 * k + 1], T, eps, &d);
+        const float mu = h2[hpix * 2 * C + c + k];
+        const float ls = h2[hpix * 2 * C + C + c + k];
+        float dpdy, dpdsb, sigma;
+        const float p = gauss_likelihood_one(yt, mu, ls, &dpdy, &dpdsb, &sigma);
+        const float pc = fmaxf(p, 1e-9f);
+        nll += -logf(pc);
+        yt_act[e] = from_f32<AT>(yt);
+        if (g_rate) {
+          const float gp = -rate_scale / pc;  // upstream of p: always negative -> the likelihood bound passes it
+          g_rate[e] = gp * dpdy;
+          dy[e] = d;
+          const float gsb = gp * dpdsb;
+          // lower_bound(sigma, 0.11): pass iff sigma >= bound or gradient < 0 (math_ops.py:74-76)
+          const float gsig = (sigma >= 0.11f || gsb < 0.0f) ? gsb : 0.0f;
+          g_h2[hpix * 2 * C + c + k] = from_f32<AT>(-gp * dpdy);
+          g_h2[hpix * 2 * C + C + c + k] = from_f32<AT>(gsig * sigma);
+        }
+      }
+    } else if (g_h2) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        g_h2[hpix * 2 * C + c + k] = from_f32<AT>(0.0f);
+        g_h2[hpix * 2 * C + C + c + k] = from_f32<AT>(0.0f);
+      }
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const long long img0 = __shfl_sync(full, img, 0);
+  const bool uniform = __all_sync(full, img == img0);
+  if (uniform) {
+    const float s = warp_sum(nll);
+    if ((threadIdx.x & 31) == 0 && img0 >= 0) atomicAdd(bits + img0, static_cast<double>(s));
+  } else if (img >= 0) {
+    atomicAdd(bits + img, static_cast<double>(nll));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: distortion.  xt [N,Ho,Wo,3] (fp32) is the un-cropped output of g_s; x [N,H,W,3].
+//   sse[n]   += (x - xt)^2                         (float reconstruction, sga.py:150)
+//   sse_r[n] += (255 x - round(clip(xt,0,1) 255))^2 (sga.py:167-174)
+//   gx = grad_scale * (xt - x) inside the crop, 0 outside (sga.py:123)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_distortion(const float* __restrict__ x, const float* __restrict__ xt, int N, int H, int W, int Ho,
+                             int Wo, float grad_scale, float* __restrict__ gx, double* __restrict__ sse,
+                             double* __restrict__ sse_r) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over [N,Ho,Wo] pixels
+  const long long npix = static_cast<long long>(N) * Ho * Wo;
+  float s = 0.0f, sr = 0.0f;
+  long long img = -1;
+  if (idx < npix) {
+    const int j = static_cast<int>(idx % Wo);
+    const long long t = idx / Wo;
+    const int i = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    img = n;
+    const bool inside = (i < H && j < W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = 0.0f;
+      if (inside) {
+        const float xv = x[((static_cast<long long>(n) * H + i) * W + j) * 3 + c];
+        const float tv = xt[idx * 3 + c];
+        const float d = tv - xv;
+        s += d * d;
+        const float r = rintf(fminf(fmaxf(tv, 0.0f), 1.0f) * 255.0f) - xv * 255.0f;
+        sr += r * r;
+        g = grad_scale * d;
+      }
+      if (gx) gx[idx * 3 + c] = g;
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const long long img0 = __shfl_sync(full, img, 0);
+  const bool uniform = __all_sync(full, img == img0);
+  if (uniform) {
+    const float a = warp_sum(s), b = warp_sum(sr);
+    if ((threadIdx.x & 31) == 0 && img0 >= 0) {
+      atomicAdd(sse + img0, static_cast<double>(a));
+      atomicAdd(sse_r + img0, static_cast<double>(b));
+    }
+  } else if (img >= 0) {
+    atomicAdd(sse + img, static_cast<double>(s));
+    atomicAdd(sse_r + img, static_cast<double>(sr));
+  }
+}
+
+// stats_out (sga_b200.h): rd_loss, train_mse, train_bpp, then per image psnr, y_bpp, z_bpp, sse, mse_rounded
+__global__ void k_finalize_stats(const double* __restrict__ acc, int N, int n_ref, int H, int W, float lmbda,
+                                 float* __restrict__ out) {
+  // acc: [0,N) y nats, [N,2N) z nats, [2N,3N) sse, [3N,4N) sse rounded
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double npix = static_cast<double>(H) * W;
+  const double ln2 = 0.69314718055994530942;
+  double bpp_sum = 0.0, sse_sum = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const double yb = acc[n] / (ln2 * npix), zb = acc[N + n] / (ln2 * npix);
+    const double mse_r = acc[3 * N + n] / (npix * 3.0);
+    out[3 + 5 * n + 0] = static_cast<float>(20.0 * log10(255.0) - 10.0 * log10(mse_r));
+    out[3 + 5 * n + 1] = static_cast<float>(yb);
+    out[3 + 5 * n + 2] = static_cast<float>(zb);
+    out[3 + 5 * n + 3] = static_cast<float>(acc[2 * N + n]);
+    out[3 + 5 * n + 4] = static_cast<float>(mse_r);
+    bpp_sum += yb + zb;
+    sse_sum += acc[2 * N + n];
+  }
+  const double train_mse = sse_sum / (static_cast<double>(n_ref) * npix * 3.0) * 65025.0;
+  const double train_bpp = bpp_sum / n_ref;
+  out[0] = static_cast<float>(lmbda > 0.0f ? lmbda * train_mse + train_bpp : train_bpp);
+  out[1] = static_cast<float>(train_mse);
+  out[2] = static_cast<float>(train_bpp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: Adam (adam.py:36-57).  g = (ga + gb) * fac  (the two gradient contributions of a latent times the soft-round
+// derivative); separate roundings (no FMA contraction) to follow numpy's float32 arithmetic.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
+                       const float* __restrict__ gb, const float* __restrict__ fac, long long numel, float lr_t,
+                       float b1, float omb1, float b2, float omb2, float eps, float* __restrict__ g_out) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= numel) return;
+  float g = ga[e];
+  if (gb) g = __fadd_rn(g, gb[e]);
+  if (fac) g = __fmul_rn(g, fac[e]);
+  if (g_out) g_out[e] = g;
+  if (p == nullptr) return;
+  const float mt = __fadd_rn(__fmul_rn(b1, m[e]), __fmul_rn(omb1, g));
+  const float vt = __fadd_rn(__fmul_rn(b2, v[e]), __fmul_rn(omb2, __fmul_rn(g, g)));
+  const float den = __fadd_rn(__fsqrt_rn(vt), eps);
+  p[e] = __fsub_rn(p[e], __fdiv_rn(__fmul_rn(lr_t, mt), den));
+  m[e] = mt;
+  v[e] = vt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point-wise pieces of (I)GDN for the fp32 path
+// ------------------------------------------------------------------------------------------------
+__global__ void k_square(const float* __restrict__ x, long long n, float* __restrict__ o) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n) o[e] = x[e] * x[e];
+}
+// nrm = beta + x^2 @ gamma (bias already added by the GEMM). inverse: out = x*sqrt(nrm) else x/sqrt(nrm)
+__global__ void k_gdn_finish(const float* __restrict__ x, const float* __restrict__ nrm, long long n, int inverse,
+                             float* __restrict__ out, float* __restrict__ s_out) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  const float s = sqrtf(nrm[e]);
+  out[e] = inverse ? x[e] * s : x[e] / s;
+  if (s_out) s_out[e] = s;
+}
+__global__ void k_igdn_bwd_pre(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ s,
+                               long long n, float* __restrict__ t) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n) t[e] = g[e] * x[e] / s[e];
+}
+__global__ void k_igdn_bwd_finish(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ s,
+                                  const float* __restrict__ u, long long n, float* __restrict__ gx) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n) gx[e] = g[e] * s[e] + x[e] * u[e];
+}
+
+template <typename TI, typename TO>
+__global__ void k_convert(const TI* __restrict__ in, long long n, TO* __restrict__ out) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n) out[e] = from_f32<TO>(to_f32<TI>(in[e]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(long long n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+int launch_soft_round(const float* v, const float* inj, long long numel, float T, float eps, uint64_t seed, int step,
+                      int tensor_id, float* vt, float* dvt, cudaStream_t st) {
+  if (numel <= 0) return SGA_OK;
+  const long long pairs = (numel + 1) / 2;
+  k_soft_round<<<blocks_for(pairs, 256), 256, 0, st>>>(v, inj, numel, T, eps, seed, step, tensor_id, vt, dvt);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_eb_pack(const float* const m[4], const float* const b[4], const float* const f[3], int C, float* pk,
+                   cudaStream_t st) {
+  k_eb_pack<<<blocks_for(C, 128), 128, 0, st>>>(m[0], m[1], m[2], m[3], b[0], b[1], b[2], b[3], f[0], f[1], f[2], C, pk);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_eb_likelihood(const float* zt, long long numel, int C, const float* pk, float* p, float* dp,
+                         cudaStream_t st) {
+  if (numel <= 0) return SGA_OK;
+  k_eb_likelihood<<<blocks_for(numel, 256), 256, 0, st>>>(zt, numel, C, pk, p, dp);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, long long numel, float* p, float* dpdy,
+                            float* dpdsb, cudaStream_t st) {
+  if (numel <= 0) return SGA_OK;
+  k_gauss_likelihood<<<blocks_for(numel, 256), 256, 0, st>>>(yt, mu, ls, numel, p, dpdy, dpdsb);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+template <typename AT>
+int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
+                  float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
+                  float* dz, double* bits, cudaStream_t st) {
+  const long long pairs = (numel + 1) / 2;
+  k_z_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(z, inj, numel, per_image, C, pk, T, eps, seed, step, hard,
+                                                       rate_scale, zt_act, g_rate, dz, bits);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+template int launch_z_path<float>(const float*, const float*, long long, long long, int, const float*, float, float,
+                                  uint64_t, int, int, float, float*, float*, float*, double*, cudaStream_t);
+template int launch_z_path<__nv_bfloat16>(const float*, const float*, long long, long long, int, const float*, float,
+                                          float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*, double*,
+                                          cudaStream_t);
+
+template <typename AT>
+int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
+                  float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
+                  float* dy, AT* g_h2, double* bits, cudaStream_t st) {
+  const long long pairs = static_cast<long long>(N) * Hh * Wh * (C / 2);
+  k_y_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step, hard,
+                                                       rate_scale, yt_act, g_rate, dy, g_h2, bits);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+template int launch_y_path<float>(const float*, const float*, const float*, int, int, int, int, int, int, float, float,
+                                  uint64_t, int, int, float, float*, float*, float*, float*, double*, cudaStream_t);
+template int launch_y_path<__nv_bfloat16>(const float*, const float*, const float*, int, int, int, int, int, int, float,
+                                          float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*,
+                                          __nv_bfloat16*, double*, cudaStream_t);
+
+int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
+                      double* sse, double* sse_r, cudaStream_t st) {
+  const long long npix = static_cast<long long>(N) * Ho * Wo;
+  k_distortion<<<blocks_for(npix, 256), 256, 0, st>>>(x, xt, N, H, W, Ho, Wo, grad_scale, gx, sse, sse_r);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st) {
+  k_finalize_stats<<<1, 32, 0, st>>>(acc, N, n_ref, H, W, lmbda, out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, const float* fac, long long numel,
+                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st) {
+  if (numel <= 0) return SGA_OK;
+  const double t = iterations + 1.0;
+  const double lr_t = lr * (sqrt(1.0 - pow(beta2, t)) / (1.0 - pow(beta1, t)));  // adam.py:40-42 (float64 scalar)
+  k_adam<<<blocks_for(numel, 256), 256, 0, st>>>(p, m, v, ga, gb, fac, numel, static_cast<float>(lr_t),
+                                                 static_cast<float>(beta1), static_cast<float>(1.0 - beta1),
+                                                 static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+                                                 static_cast<float>(eps), g_out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_square(const float* x, long long n, float* o, cudaStream_t st) {
+  k_square<<<blocks_for(n, 256), 256, 0, st>>>(x, n, o);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+int launch_gdn_finish(const float* x, const float* nrm, long long n, int inverse, float* out, float* s_out,
+                      cudaStream_t st) {
+  k_gdn_finish<<<blocks_for(n, 256), 256, 0, st>>>(x, nrm, n, inverse, out, s_out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+int launch_igdn_bwd_pre(const float* g, const float* x, const float* s, long long n, float* t, cudaStream_t st) {
+  k_igdn_bwd_pre<<<blocks_for(n, 256), 256, 0, st>>>(g, x, s, n, t);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+int launch_igdn_bwd_finish(const float* g, const float* x, const float* s, const float* u, long long n, float* gx,
+                           cudaStream_t st) {
+  k_igdn_bwd_finish<<<blocks_for(n, 256), 256, 0, st>>>(g, x, s, u, n, gx);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t st) {
+  if (n <= 0) return SGA_OK;
+  k_convert<float, __nv_bfloat16><<<blocks_for(n, 256), 256, 0, st>>>(in, n, out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t st) {
+  if (n <= 0) return SGA_OK;
+  k_convert<__nv_bfloat16, float><<<blocks_for(n, 256), 256, 0, st>>>(in, n, out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+}  // namespace sga

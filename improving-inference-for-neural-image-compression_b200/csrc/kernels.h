@@ -1,0 +1,83 @@
+// kernels.h -- host-side launchers shared between the translation units of libsga_b200.so
+#pragma once
+#include "common.cuh"
+
+namespace sga {
+
+constexpr int TENSOR_ID_Y = 1;  // Philox counter word 2 (oracle/sga_oracle.py TENSOR_ID_*)
+constexpr int TENSOR_ID_Z = 2;
+
+// ---- elementwise.cu
+int launch_soft_round(const float* v, const float* inj, long long numel, float T, float eps, uint64_t seed, int step,
+                      int tensor_id, float* vt, float* dvt, cudaStream_t st);
+int launch_eb_pack(const float* const m[4], const float* const b[4], const float* const f[3], int C, float* pk,
+                   cudaStream_t st);
+int launch_eb_likelihood(const float* zt, long long numel, int C, const float* pk, float* p, float* dp, cudaStream_t st);
+int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, long long numel, float* p, float* dpdy,
+                            float* dpdsb, cudaStream_t st);
+template <typename AT>
+int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
+                  float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
+                  float* dz, double* bits, cudaStream_t st);
+template <typename AT>
+int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
+                  float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
+                  float* dy, AT* g_h2, double* bits, cudaStream_t st);
+int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
+                      double* sse, double* sse_r, cudaStream_t st);
+int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st);
+int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, const float* fac, long long numel,
+                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st);
+int launch_square(const float* x, long long n, float* o, cudaStream_t st);
+int launch_gdn_finish(const float* x, const float* nrm, long long n, int inverse, float* out, float* s_out,
+                      cudaStream_t st);
+int launch_igdn_bwd_pre(const float* g, const float* x, const float* s, long long n, float* t, cudaStream_t st);
+int launch_igdn_bwd_finish(const float* g, const float* x, const float* s, const float* u, long long n, float* gx,
+                           cudaStream_t st);
+int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t st);
+int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t st);
+
+// ---- conv_plan.cu : tap tables shared by the SIMT and tcgen05 paths
+struct ConvGeom {
+  int kind, kh, kw;
+  int N, Hin, Win, Cin;    // input tensor [N,Hin,Win,Cin]
+  int Hout, Wout, Cout;    // output tensor
+};
+// A job = one dense multi-tap accumulation into one output view.
+struct ConvJobPlan {
+  int nviews;
+  int view_py[kMaxViews], view_px[kMaxViews];  // phase of each input view (stride-2 sub-grids) or 0,0
+  int in_phase_stride;                          // 1 (plain) or 2 (phase views of the input)
+  int out_py, out_px, out_phase_stride;         // output view: plain (stride 1) or one phase of the 2x grid
+  int ntaps;
+  Tap taps[kMaxTaps];
+  int Ho, Wo;                                   // pixel grid of this job's output view
+};
+struct ConvPlan {
+  ConvGeom g;
+  int njobs;
+  ConvJobPlan job[4];
+  bool w_transposed;  // B operand is kernel[tap]^T (dgrad kinds)
+};
+int make_conv_plan(int kind, int kh, int kw, int N, int Hin, int Win, int Cin, int Cout_kernel, ConvPlan* plan);
+
+// ---- conv_simt.cu : fp32 implicit GEMM on CUDA cores (init, final eval, cross-checks)
+// w: [taps][K][Nn] with K = contraction channels, Nn = output channels of the op (already transposed for dgrads)
+int launch_conv_simt(const ConvPlan& plan, const float* x, const float* w, const float* bias, const float* relu_mask,
+                     int relu, float* out, cudaStream_t st);
+// w_ref (kh,kw,Cin,Cout) -> [tap][Cout][Cin]
+int launch_transpose_taps(const float* w_ref, int taps, int Cin, int Cout, float* w_t, cudaStream_t st);
+
+// ---- conv_tc.cu : bf16 tcgen05 implicit GEMM
+struct TcConv;  // opaque: tensor maps + tap tables for one layer at one shape
+int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, TcConv** out);
+void tc_conv_destroy(TcConv* c);
+// epilogue: v = acc + bias[n]; relu; *= (mask > 0); store as bf16 (out_bf16) and/or fp32 (out_f32)
+int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bfloat16* relu_mask, __nv_bfloat16* out_bf16,
+                   float* out_f32, cudaStream_t st);
+// w_ref (kh,kw,Cin,Cout) fp32 -> K-major bf16 B operand: [tap][Nn][K] (K = Cin for forward kinds, Cout for dgrads)
+int launch_pack_weights_bf16(const float* w_ref, int taps, int Cin, int Cout, bool transposed, __nv_bfloat16* out,
+                             cudaStream_t st);
+int tc_selftest_available();
+
+}  // namespace sga

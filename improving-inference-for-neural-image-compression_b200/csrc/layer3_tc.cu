@@ -1,0 +1,476 @@
+// layer3_tc.cu -- the last synthesis layer (5x5 stride-2 transposed conv, C -> 3 channels; nn_models.py:60-63),
+// fused with the distortion term (sga.py:150-154, 167-174), and its dgrad (3 -> C).
+//
+// With only 3 output channels the per-phase implicit GEMM would have N = 3.  Instead:
+//   forward ("scatter" form): P[pixel, (a,b,c)] = sum_cin act[pixel, cin] * k[a,b,cin,c]   -- one GEMM with
+//     M = 128 input pixels, K = C, N = 75 (padded to 80); the epilogue overlap-adds the 5x5x3 patches (col2im) in
+//     shared memory: out[2i+a-2, 2j+b-2, c] += P[(i,j),(a,b,c)].  Tiles carry a 1-pixel halo (8x16 loaded, 6x14
+//     interior) so every output pixel is completed inside one CTA; the finished x_tilde values are compared with x
+//     on the spot: SSE, rounded-SSE (PSNR) and d loss / d x_tilde (bf16, [N,Ho,Wo,4]) leave the kernel.
+//   dgrad ("gather" form):  g_act[pixel, cin] = sum_{a,b,c} gx[2i+a-2, 2j+b-2, c] * k[a,b,cin,c]  -- M = 128 input
+//     pixels, K = 75 (padded to 80), N = C.  The im2col A operand is built by 4 warps from a shared-memory copy of
+//     the gradient patch, directly in the no-swizzle K-major core-matrix layout the tensor core reads.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace sga {
+
+using namespace tc;
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+constexpr int kL3Threads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kL3Stages = 5;
+constexpr int kL3NPad = 80;
+constexpr int kPsStride = 81;
+constexpr int kL3IntH = 6, kL3IntW = 14;   // interior of the 8x16 tile
+
+struct alignas(64) L3FwdParams {
+  CUtensorMap amap;   // activation [N,Hin,Win,C] bf16
+  CUtensorMap bmap;   // scatter weights [80][C] bf16
+  const float* x;     // image [N,H,W,3]
+  float* xt_out;      // optional x_tilde [N,2Hin,2Win,3]
+  __nv_bfloat16* gx;  // optional d loss / d x_tilde [N,2Hin,2Win,4]
+  double* sse;        // [N]
+  double* sse_r;      // [N]
+  float bias[3];
+  float grad_scale;
+  int N, Hin, Win, C, H, W;
+  int tiles_h, tiles_w, total_tiles, kchunks;
+};
+
+__global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant__ L3FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int b_chunk = kL3NPad * 128;                 // 10240
+  const uint32_t b_base = base;
+  const uint32_t a_base = base + P.kchunks * b_chunk;
+  uint8_t* p_after = smem + P.kchunks * b_chunk + kL3Stages * 16384;
+  float* Ps = reinterpret_cast<float*>(p_after);     // [2][128][81]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_after + 2 * 128 * kPsStride * 4);
+  const uint32_t bar_b = smem_u32(bars);
+  const uint32_t bar_full = bar_b + 8;
+  const uint32_t bar_empty = bar_full + 8 * kL3Stages;
+  const uint32_t bar_tfull = bar_empty + 8 * kL3Stages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kL3Stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.amap);
+    tma_prefetch_desc(&P.bmap);
+    mbar_init(bar_b, 1);
+    for (int s = 0; s < kL3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), 256); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int tiles_per_img = P.tiles_h * P.tiles_w;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_b, P.kchunks * b_chunk);
+      for (int kc = 0; kc < P.kchunks; ++kc) tma_load_2d(b_base + kc * b_chunk, &P.bmap, bar_b, kc * 64, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, 16384);
+          tma_load_4d(a_base + stage * 16384, &P.amap, bar_full + 8 * stage, kc * 64, w0, h0, img);
+          if (++stage == kL3Stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_bf16(128, kL3NPad);
+      mbar_wait(bar_b, 0);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(d_tmem, smem_desc_sw128(a_base + stage * 16384 + kk * 32),
+                      smem_desc_sw128(b_base + kc * b_chunk + kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == kL3Stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;        // 0..127 among epilogue threads
+    const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
+    float acc_s = 0.0f, acc_r = 0.0f;
+    int acc_img = -1;
+    auto flush = [&]() {
+      const float a = warp_sum(acc_s), b = warp_sum(acc_r);
+      if (lane == 0 && acc_img >= 0) {
+        atomicAdd(P.sse + acc_img, static_cast<double>(a));
+        atomicAdd(P.sse_r + acc_img, static_cast<double>(b));
+      }
+      acc_s = 0.0f; acc_r = 0.0f;
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
+      const int buf = it & 1;
+      if (img != acc_img) { flush(); acc_img = img; }   // warp-uniform
+      float* Pb = Ps + buf * 128 * kPsStride;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
+      {
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + k] = __uint_as_float(r[k]);
+        tmem_ld32(taddr + 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + 32 + k] = __uint_as_float(r[k]);
+        uint32_t r2[16];
+        tmem_ld16(taddr + 64, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 64 + k] = __uint_as_float(r2[k]);
+      }
+      tcgen05_fence_before();
+      named_bar_sync(1, 128);                 // all 128 rows of P are in shared memory; TMEM buffer drained
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      // ---- col2im + distortion: 12 x 28 output pixels of this tile's interior
+      for (int p = et; p < 2 * kL3IntH * 2 * kL3IntW; p += 128) {
+        const int ry = p / (2 * kL3IntW), rx = p % (2 * kL3IntW);
+        const int oy = 2 * hi0 + ry, ox = 2 * wi0 + rx;
+        if (oy >= Ho || ox >= Wo) continue;
+        const int py = ry & 1, px = rx & 1;
+        const int tr = (ry >> 1) + 1, tcx = (rx >> 1) + 1;   // tile coordinates of the co-located input pixel
+        float v0 = P.bias[0], v1 = P.bias[1], v2 = P.bias[2];
+        // out[2i'+py] takes k[a], a = py + 2 - 2o, from input row i'+o (conv_plan.cu)
+#pragma unroll
+        for (int oyy = 1; oyy >= -1; --oyy) {
+          const int a = py + 2 - 2 * oyy;
+          if (a < 0 || a > 4) continue;
+#pragma unroll
+          for (int oxx = 1; oxx >= -1; --oxx) {
+            const int b = px + 2 - 2 * oxx;
+            if (b < 0 || b > 4) continue;
+            const float* pp = Pb + ((tr + oyy) * 16 + (tcx + oxx)) * kPsStride + (a * 5 + b) * 3;
+            v0 += pp[0]; v1 += pp[1]; v2 += pp[2];
+          }
+        }
+        const long long opix = (static_cast<long long>(img) * Ho + oy) * Wo + ox;
+        if (P.xt_out) { P.xt_out[opix * 3] = v0; P.xt_out[opix * 3 + 1] = v1; P.xt_out[opix * 3 + 2] = v2; }
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (oy < P.H && ox < P.W) {
+          const float* xp = P.x + ((static_cast<long long>(img) * P.H + oy) * P.W + ox) * 3;
+          const float vv[3] = {v0, v1, v2};
+          float gg[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float xv = xp[c];
+            const float d = vv[c] - xv;
+            acc_s += d * d;
+            const float rr = rintf(fminf(fmaxf(vv[c], 0.0f), 1.0f) * 255.0f) - xv * 255.0f;
+            acc_r += rr * rr;
+            gg[c] = P.grad_scale * d;
+          }
+          g0 = gg[0]; g1 = gg[1]; g2 = gg[2];
+        }
+        if (P.gx) *reinterpret_cast<uint2*>(P.gx + opix * 4) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, 0.0f));
+      }
+    }
+    flush();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// =====================================================================================================
+// dgrad
+// =====================================================================================================
+constexpr int kL3dThreads = 288;      // warp 0 MMA, warps 1-4 builders, warps 5-8 epilogue
+constexpr int kRegH = 19, kRegW = 35; // gradient patch needed by an 8x16 input tile
+
+struct alignas(64) L3DgradParams {
+  const __nv_bfloat16* gx;     // [N,Ho,Wo,4]
+  const __nv_bfloat16* wpack;  // [10][C][8] bf16 : B operand in core-matrix order
+  __nv_bfloat16* out;          // [N,Hin,Win,C]
+  int N, Hin, Win, C;
+  int tiles_h, tiles_w, total_tiles;
+};
+
+__global__ void __launch_bounds__(kL3dThreads, 1) k_l3_dgrad(const __grid_constant__ L3DgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int b_bytes = 10 * P.C * 16;
+  const int a_bytes = 10 * 128 * 16;                 // 20480
+  const int reg_bytes = ((kRegH * kRegW * 8 + 127) / 128) * 128;
+  const uint32_t b_base = base;
+  const uint32_t a_base = base + ((b_bytes + 1023) / 1024) * 1024;
+  uint8_t* a_ptr = smem + ((b_bytes + 1023) / 1024) * 1024;
+  uint8_t* reg_ptr = a_ptr + 2 * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reg_ptr + 2 * reg_bytes);
+  const uint32_t bar_afull = smem_u32(bars);         // [2] count 128
+  const uint32_t bar_aempty = bar_afull + 16;        // [2] commit
+  const uint32_t bar_tfull = bar_aempty + 16;        // [2] commit
+  const uint32_t bar_tempty = bar_tfull + 16;        // [2] count 4
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // resident B operand: straight copy (already in core-matrix order)
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(P.wpack) + i);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_afull + 8 * b, 128); mbar_init(bar_aempty + 8 * b, 1);
+        mbar_init(bar_tfull + 8 * b, 1);   mbar_init(bar_tempty + 8 * b, 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int tiles_per_img = P.tiles_h * P.tiles_w;
+  const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_bf16(128, P.C);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * buf, ph ^ 1u);
+        mbar_wait(bar_afull + 8 * buf, ph);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+          const uint64_t ad = smem_desc_interleave(a_base + buf * a_bytes + ks * 2 * 2048, 2048, 128);
+          const uint64_t bd = smem_desc_interleave(b_base + ks * 2 * (P.C * 16), P.C * 16, 128);
+          umma_bf16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_aempty + 8 * buf);
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else if (warp <= 4) {
+    // ---------------- builders: gradient patch -> im2col A operand ----------------
+    const int bt = threadIdx.x - 32;    // 0..127 == tile row
+    const int tr = bt >> 4, tcx = bt & 15;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
+      uint2* reg = reinterpret_cast<uint2*>(reg_ptr + buf * reg_bytes);
+      // region origin (2*h0-2, 2*w0-2); the previous user of reg[buf]/A[buf] was tile it-2
+      mbar_wait(bar_aempty + 8 * buf, ph ^ 1u);
+      for (int e = bt; e < kRegH * kRegW; e += 128) {
+        const int ry = e / kRegW, rx = e % kRegW;
+        const int gy = 2 * h0 - 2 + ry, gxx = 2 * w0 - 2 + rx;
+        uint2 v = make_uint2(0u, 0u);
+        if (gy >= 0 && gy < Ho && gxx >= 0 && gxx < Wo)
+          v = __ldg(reinterpret_cast<const uint2*>(P.gx + ((static_cast<long long>(img) * Ho + gy) * Wo + gxx) * 4));
+        reg[e] = v;
+      }
+      named_bar_sync(2, 128);
+      // row bt = input pixel (tr, tcx): 25 patch pixels x 3 channels = 75 K values (+5 zeros)
+      uint16_t kv[80];
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          const uint2 v = reg[(2 * tr + a) * kRegW + (2 * tcx + b)];
+          kv[(a * 5 + b) * 3 + 0] = static_cast<uint16_t>(v.x & 0xFFFFu);
+          kv[(a * 5 + b) * 3 + 1] = static_cast<uint16_t>(v.x >> 16);
+          kv[(a * 5 + b) * 3 + 2] = static_cast<uint16_t>(v.y & 0xFFFFu);
+        }
+#pragma unroll
+      for (int k = 75; k < 80; ++k) kv[k] = 0;
+      uint8_t* ab = a_ptr + buf * a_bytes;
+#pragma unroll
+      for (int gq = 0; gq < 10; ++gq) {
+        uint4 o;
+        o.x = kv[gq * 8 + 0] | (static_cast<uint32_t>(kv[gq * 8 + 1]) << 16);
+        o.y = kv[gq * 8 + 2] | (static_cast<uint32_t>(kv[gq * 8 + 3]) << 16);
+        o.z = kv[gq * 8 + 4] | (static_cast<uint32_t>(kv[gq * 8 + 5]) << 16);
+        o.w = kv[gq * 8 + 6] | (static_cast<uint32_t>(kv[gq * 8 + 7]) << 16);
+        *reinterpret_cast<uint4*>(ab + gq * 2048 + bt * 16) = o;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_afull + 8 * buf);
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int i = (tt / P.tiles_w) * 8 + (row >> 4), j = (tt % P.tiles_w) * 16 + (row & 15);
+      const bool valid = (i < P.Hin) && (j < P.Win);
+      const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * P.C;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      for (int col = 0; col < P.C; col += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + col, r);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(P.out + off0 + col);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            op[u] = make_uint4(pack_bf16(__uint_as_float(r[u * 8]), __uint_as_float(r[u * 8 + 1])),
+                               pack_bf16(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3])),
+                               pack_bf16(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5])),
+                               pack_bf16(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7])));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// =====================================================================================================
+// host
+// =====================================================================================================
+struct L3Tc {
+  L3FwdParams F;
+  L3DgradParams D;
+  int f_smem, f_grid, d_smem, d_grid;
+};
+
+// w_scatter: bf16 [80][C] (row n = (a*5+b)*3+c);  w_gather: bf16 [10][C][8]
+__global__ void k_l3_pack(const float* __restrict__ k3, int C, __nv_bfloat16* __restrict__ w_scatter,
+                          __nv_bfloat16* __restrict__ w_gather) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 80 * C) return;
+  const int n = e / C, ci = e % C;
+  float v = 0.0f;
+  if (n < 75) {
+    const int tap = n / 3, c = n % 3;
+    v = k3[(static_cast<long long>(tap) * C + ci) * 3 + c];
+  }
+  w_scatter[e] = __float2bfloat16_rn(v);
+  w_gather[(static_cast<long long>(n >> 3) * C + ci) * 8 + (n & 7)] = __float2bfloat16_rn(v);
+}
+
+int l3_pack_weights(const float* k3, int C, __nv_bfloat16* w_scatter, __nv_bfloat16* w_gather, cudaStream_t st) {
+  k_l3_pack<<<(80 * C + 255) / 256, 256, 0, st>>>(k3, C, w_scatter, w_gather);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const __nv_bfloat16* w_gather, int N, int Hin,
+                 int Win, int C, int H, int W, L3Tc** out) {
+  SGA_CHECK(C % 64 == 0 && C <= 256, "tcgen05 layer-3 kernels need C %% 64 == 0 and <= 256 (got %d)", C);
+  L3Tc* c = new L3Tc();
+  memset(c, 0, sizeof(*c));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    L3FwdParams& F = c->F;
+    F.N = N; F.Hin = Hin; F.Win = Win; F.C = C; F.H = H; F.W = W;
+    F.kchunks = C / 64;
+    F.tiles_h = ceil_div(Hin, kL3IntH); F.tiles_w = ceil_div(Win, kL3IntW);
+    F.total_tiles = N * F.tiles_h * F.tiles_w;
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                              static_cast<uint64_t>(N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Win) * C * 2,
+                                 static_cast<uint64_t>(Hin) * Win * C * 2};
+    const uint32_t box[4] = {64, 16, 8, 1};
+    int st = tma_encode_tiled(&F.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, act, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st != SGA_OK) { delete c; return st; }
+    const uint64_t bdims[2] = {static_cast<uint64_t>(C), 80};
+    const uint64_t bstr[1] = {static_cast<uint64_t>(C) * 2};
+    const uint32_t bbox[2] = {64, 80};
+    st = tma_encode_tiled(&F.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_scatter, bdims, bstr, bbox,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st != SGA_OK) { delete c; return st; }
+    c->f_smem = 1024 + F.kchunks * kL3NPad * 128 + kL3Stages * 16384 + 2 * 128 * kPsStride * 4 + 256;
+    c->f_grid = F.total_tiles < sms ? F.total_tiles : sms;
+  }
+  {
+    L3DgradParams& D = c->D;
+    D.N = N; D.Hin = Hin; D.Win = Win; D.C = C; D.wpack = w_gather;
+    D.tiles_h = ceil_div(Hin, 8); D.tiles_w = ceil_div(Win, 16);
+    D.total_tiles = N * D.tiles_h * D.tiles_w;
+    const int b_bytes = 10 * C * 16;
+    const int reg_bytes = ((kRegH * kRegW * 8 + 127) / 128) * 128;
+    c->d_smem = 1024 + ((b_bytes + 1023) / 1024) * 1024 + 2 * 20480 + 2 * reg_bytes + 256;
+    c->d_grid = D.total_tiles < sms ? D.total_tiles : sms;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  *out = c;
+  return SGA_OK;
+}
+
+void l3_tc_destroy(L3Tc* c) { delete c; }
+
+int l3_tc_forward(const L3Tc* c, const float* bias_dev_host3, const float* x, float grad_scale, float* xt_out,
+                  __nv_bfloat16* gx, double* sse, double* sse_r, cudaStream_t st) {
+  if (c->F.total_tiles == 0) return SGA_OK;
+  L3FwdParams F = c->F;
+  F.bias[0] = bias_dev_host3[0]; F.bias[1] = bias_dev_host3[1]; F.bias[2] = bias_dev_host3[2];
+  F.x = x; F.grad_scale = grad_scale; F.xt_out = xt_out; F.gx = gx; F.sse = sse; F.sse_r = sse_r;
+  k_l3_fwd<<<c->f_grid, kL3Threads, c->f_smem, st>>>(F);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int l3_tc_dgrad(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cudaStream_t st) {
+  if (c->D.total_tiles == 0) return SGA_OK;
+  L3DgradParams D = c->D;
+  D.gx = gx; D.out = out;
+  k_l3_dgrad<<<c->d_grid, kL3dThreads, c->d_smem, st>>>(D);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+}  // namespace sga

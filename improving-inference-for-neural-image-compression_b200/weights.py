@@ -1,0 +1,216 @@
+"""Model weights in the reference's checkpoint layout.
+
+The reference restores a TF1 checkpoint from ``<checkpoint_dir>/<runname>/`` (sga.py:180-182,
+tf_boilerplate.py:47-48) whose variables are created by the Keras layers in nn_models.py.  This
+module keeps that directory layout and those variable names; the container is ``model.npz``
+(one array per variable) because TensorFlow is not available to write/read V2 bundles here.
+
+Variable names (Keras TF1 scopes):
+  analysis_transform/layer_{0..3}/{kernel|kernel_rdft, bias}, layer_{0..2}/gdn_{i}/{beta|reparam_beta, gamma|reparam_gamma}
+  synthesis_transform/layer_{0..3}/{kernel|kernel_rdft, bias}, layer_{0..2}/igdn_{i}/{...}
+  hyper_analysis_transform/layer_{0,1}/{kernel|kernel_rdft, bias}, layer_2/{kernel|kernel_rdft}   (no bias, nn_models.py:95)
+  mb_t2018hyper_synthesis_transform/layer_{0..2}/{kernel, bias}                                  (kernel_parameterizer=None, nn_models.py:154)
+  entropy_bottleneck/{matrix_0..3, bias_0..3, factor_0..2}
+Kernels are (kh, kw, Cin, Cout) like tfc.SignalConv2D; gamma is (in, out).
+Re-parameterised variables (``kernel_rdft``, ``reparam_beta``, ``reparam_gamma``) are converted on load.
+"""
+import os
+
+import numpy as np
+
+GA = "analysis_transform/layer_%d/"
+GS = "synthesis_transform/layer_%d/"
+HA = "hyper_analysis_transform/layer_%d/"
+HS = "mb_t2018hyper_synthesis_transform/layer_%d/"
+EB = "entropy_bottleneck/"
+
+GDN_PEDESTAL = 2.0 ** -36          # tfc.NonnegativeParameterizer reparam_offset = 2**-18, pedestal = offset**2
+GDN_BETA_MIN = 1e-6
+GDN_GAMMA_MIN = 0.0
+
+
+def variable_shapes(C, hyper_mid=None):
+    """name -> shape for the mean-scale hyperprior at `C` filters (sga.py:70-74, nn_models.py)."""
+    mid = int(C * 1.5) if hyper_mid is None else hyper_mid       # nn_models.py:157
+    s = {}
+    for i, (ci, co) in enumerate([(3, C), (C, C), (C, C), (C, C)]):
+        s[(GA % i) + "kernel"] = (5, 5, ci, co)
+        s[(GA % i) + "bias"] = (co,)
+        if i < 3:
+            s[(GA % i) + "gdn_%d/beta" % i] = (co,)
+            s[(GA % i) + "gdn_%d/gamma" % i] = (co, co)
+    for i, (ci, co) in enumerate([(C, C), (C, C), (C, C), (C, 3)]):
+        s[(GS % i) + "kernel"] = (5, 5, ci, co)
+        s[(GS % i) + "bias"] = (co,)
+        if i < 3:
+            s[(GS % i) + "igdn_%d/beta" % i] = (co,)
+            s[(GS % i) + "igdn_%d/gamma" % i] = (co, co)
+    s[(HA % 0) + "kernel"] = (3, 3, C, C)
+    s[(HA % 0) + "bias"] = (C,)
+    s[(HA % 1) + "kernel"] = (5, 5, C, C)
+    s[(HA % 1) + "bias"] = (C,)
+    s[(HA % 2) + "kernel"] = (5, 5, C, C)
+    s[(HS % 0) + "kernel"] = (5, 5, C, C)
+    s[(HS % 0) + "bias"] = (C,)
+    s[(HS % 1) + "kernel"] = (5, 5, C, mid)
+    s[(HS % 1) + "bias"] = (mid,)
+    s[(HS % 2) + "kernel"] = (3, 3, mid, 2 * C)
+    s[(HS % 2) + "bias"] = (2 * C,)
+    dims = (1, 3, 3, 3, 1)                                        # tfc EntropyBottleneck filters=(3,3,3)
+    for i in range(4):
+        s[EB + "matrix_%d" % i] = (C, dims[i + 1], dims[i])       # learned_prior.py:45-47
+        s[EB + "bias_%d" % i] = (C, dims[i + 1], 1)               # :53-56
+        if i < 3:
+            s[EB + "factor_%d" % i] = (C, dims[i + 1], 1)         # :60-63
+    return s
+
+
+def make_synthetic(C, seed=0):
+    """Random-init weights with realistic statistics (no trained checkpoint is reachable offline):
+    variance-preserving (de)conv kernels, beta ~ 1, gamma ~ 0.1 I + small positive, and the
+    EntropyBottleneck initialisation of learned_prior.py:36-66 (init_scale=10) plus jitter."""
+    rng = np.random.default_rng(seed)
+    W = {}
+    for name, shp in variable_shapes(C).items():
+        leaf = name.split("/")[-1]
+        if leaf == "kernel":
+            kh, kw, ci, co = shp
+            up = name.startswith(GS[:10]) or (name.startswith(HS[:10]) and kh == 5)
+            taps = kh * kw / (4.0 if up else 1.0)                  # stride-2 deconv: ~25/4 taps per output
+            std = (1.0 / (taps * ci)) ** 0.5
+            if name == (GA % 3) + "kernel":
+                std *= 6.0                                         # latents y with a spread of a few integers
+            if name == (HA % 2) + "kernel":
+                std *= 3.0
+            if name == (GS % 0) + "kernel":
+                std *= 0.55                                        # compensate the spread of y
+            if name in ((GS % 1) + "kernel", (GS % 2) + "kernel"):
+                std *= 0.75                                        # IGDN expands by ~1.3x per stage
+            if name == (GS % 3) + "kernel":
+                std *= 0.2                                         # reconstructions with a spread of ~0.2
+            W[name] = (rng.standard_normal(shp) * std).astype(np.float32)
+        elif leaf == "bias" and not name.startswith(EB):
+            b = rng.standard_normal(shp) * 0.05
+            if name == (GS % 3) + "bias":
+                b = b + 0.45                                       # reconstructions centred in [0,1]
+            W[name] = b.astype(np.float32)
+        elif leaf == "beta":
+            W[name] = (1.0 + 0.1 * rng.random(shp)).astype(np.float32)
+        elif leaf == "gamma":
+            g = 0.1 * np.eye(shp[0]) + 0.002 * rng.random(shp)
+            W[name] = g.astype(np.float32)
+    dims = (1, 3, 3, 3, 1)
+    scale = 10.0 ** (1 / 4)
+    for i in range(4):
+        init = np.log(np.expm1(1 / scale / dims[i + 1]))
+        W[EB + "matrix_%d" % i] = (init + 0.2 * rng.standard_normal((C, dims[i + 1], dims[i]))).astype(np.float32)
+        W[EB + "bias_%d" % i] = rng.uniform(-0.5, 0.5, (C, dims[i + 1], 1)).astype(np.float32)
+        if i < 3:
+            W[EB + "factor_%d" % i] = (0.3 * rng.standard_normal((C, dims[i + 1], 1))).astype(np.float32)
+    return W
+
+
+# ---- re-parameterisations used by the reference's checkpoints -------------------------------------------
+
+def gdn_from_reparam(reparam, minimum):
+    """tfc.NonnegativeParameterizer: var = max(reparam, sqrt(minimum + pedestal))**2 - pedestal."""
+    bound = (minimum + GDN_PEDESTAL) ** 0.5
+    return (np.maximum(reparam.astype(np.float64), bound) ** 2 - GDN_PEDESTAL).astype(np.float32)
+
+
+def gdn_to_reparam(var, minimum):
+    return np.sqrt(np.maximum(var.astype(np.float64) + GDN_PEDESTAL, minimum + GDN_PEDESTAL)).astype(np.float32)
+
+
+def irdft_matrix(shape):
+    """Orthonormal real-DFT synthesis basis: (prod(shape), prod(shape)) matrix M with
+    kernel = reshape(M @ kernel_rdft, shape + (Cin, Cout)) (tfc.RDFTParameterizer).
+    UNVERIFIED against tfc 1.3's column ordering (PARITY_ASSUMPTIONS.md item P9): real checkpoints
+    must be validated before trusting this path."""
+    shape = tuple(int(s) for s in shape)
+    size = int(np.prod(shape))
+    rank = len(shape)
+    eye = np.identity(size, dtype=np.float64).reshape((size,) + shape)
+    spec = np.fft.rfftn(eye, axes=tuple(range(1, rank + 1)))
+    last = shape[-1]
+    scale = np.ones(spec.shape[-1])
+    scale[1:(last - 1) // 2 + 1] = np.sqrt(2.0)
+    spec = spec * scale / np.sqrt(size)
+    spec = spec.reshape(size, -1)
+    cols = np.concatenate([spec.real, spec.imag], axis=1)
+    # keep a maximal linearly independent set of columns, in order (Gram-Schmidt pivoting)
+    keep, basis = [], []
+    for j in range(cols.shape[1]):
+        v = cols[:, j].copy()
+        for b in basis:
+            v -= b * (b @ v)
+        n = np.linalg.norm(v)
+        if n > 1e-9:
+            basis.append(v / n)
+            keep.append(j)
+        if len(keep) == size:
+            break
+    return np.stack(basis, axis=1)
+
+
+def deparameterise(raw):
+    """Convert any `kernel_rdft` / `reparam_beta` / `reparam_gamma` entries to plain variables."""
+    W = {}
+    for name, arr in raw.items():
+        arr = np.asarray(arr)
+        head, leaf = name.rsplit("/", 1) if "/" in name else ("", name)
+        if leaf == "reparam_beta":
+            W[head + "/beta"] = gdn_from_reparam(arr, GDN_BETA_MIN)
+        elif leaf == "reparam_gamma":
+            W[head + "/gamma"] = gdn_from_reparam(arr, GDN_GAMMA_MIN)
+        elif leaf == "kernel_rdft":
+            shp = raw[head + "/kernel_shape"] if head + "/kernel_shape" in raw else None
+            if shp is None:
+                raise ValueError("kernel_rdft needs a sibling kernel_shape entry: %s" % name)
+            kh, kw, ci, co = (int(v) for v in shp)
+            W[head + "/kernel"] = (irdft_matrix((kh, kw)) @ arr.astype(np.float64)).reshape(kh, kw, ci, co).astype(np.float32)
+        elif leaf == "kernel_shape":
+            continue
+        else:
+            W[name] = arr.astype(np.float32)
+    return W
+
+
+def check_complete(W, C):
+    want = variable_shapes(C)
+    missing = [k for k in want if k not in W]
+    if missing:
+        raise KeyError("checkpoint is missing variables: %s" % ", ".join(missing[:6]))
+    for k, shp in want.items():
+        if tuple(W[k].shape) != tuple(shp):
+            raise ValueError("variable %s has shape %s, expected %s (num_filters=%d)" % (k, W[k].shape, shp, C))
+
+
+def save_checkpoint(checkpoint_dir, runname, W):
+    d = os.path.join(checkpoint_dir, runname)
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "model.npz")
+    np.savez(path, **W)
+    with open(os.path.join(d, "checkpoint"), "w") as f:          # same marker file TF writes
+        f.write('model_checkpoint_path: "model.npz"\n')
+    return path
+
+
+def load_checkpoint(checkpoint_dir, runname, num_filters):
+    """Mirror of tf.train.latest_checkpoint + Saver.restore (sga.py:180-182)."""
+    d = os.path.join(checkpoint_dir, runname)
+    path = os.path.join(d, "model.npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "no model.npz under %s (TF V2 bundles are not readable without TensorFlow; "
+            "export the variables to model.npz with the names listed in weights.py)" % d)
+    with np.load(path) as f:
+        raw = {k: f[k] for k in f.files}
+    W = deparameterise(raw)
+    check_complete(W, num_filters)
+    return W
+
+
+def runname(num_filters, lmbda, prefix="mbt2018"):
+    """utils.get_runname format (utils.py:51-69) for record_keys (num_filters, lmbda)."""
+    return "%s-num_filters=%s-lmbda=%s" % (prefix, num_filters, lmbda)

@@ -1,0 +1,140 @@
+/* sga_b200.h -- C ABI of libsga_b200.so: the Blackwell (sm_100a) implementation of the
+ * Stochastic-Gumbel-Annealing hot path of mandt-lab/improving-inference-for-neural-image-compression.
+ *
+ * The reference has no FFI; the seam this library replaces is the per-iteration
+ *     sess.run([rd_gradients, rd_loss, train_mse, train_bpp, psnr], feed {y, z, x, T})   sga.py:212-214
+ *     y, z = adam_optimizer.update([y, z], grads)                                         sga.py:215 (adam.py:20-59)
+ * plus the one-off init  sess.run([y_init, z_init])  (sga.py:207) and the final hard-rounded
+ * evaluation (sga.py:240-247).  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; tensors are NHWC, contiguous, float32
+ *  - all work is enqueued on the cudaStream_t passed in (as void*); no hidden synchronisation,
+ *    no allocation after sga_create + sga_bind_weights
+ *  - every function returns 0 on success, a negative sga_status otherwise; sga_last_error()
+ *    returns a thread-local description.  Nothing throws.
+ *  - one context per GPU; a context is not thread-safe; contexts are independent
+ */
+#ifndef SGA_B200_H_
+#define SGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SGA_OK = 0,
+  SGA_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  SGA_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  SGA_ERR_STATE = -3,     /* e.g. weights not bound */
+  SGA_ERR_NOMEM = -4
+} sga_status;
+
+/* arithmetic of the (de)conv stacks inside the loop */
+typedef enum {
+  SGA_OPERAND_F32 = 0,   /* fp32 SIMT kernels: init (sga.py:207), final eval (sga.py:244-247), checking */
+  SGA_OPERAND_BF16 = 1   /* bf16 operands, fp32 accumulate in TMEM: tcgen05 implicit-GEMM kernels */
+} sga_operand;
+
+typedef struct {
+  int32_t n_images;        /* images resident on this GPU (the shard) */
+  int32_t height, width;   /* image size (sga.py:51) */
+  int32_t num_filters;     /* --num_filters C (sga.py:70-73) */
+  int32_t n_ref;           /* size of the REFERENCE batch these images belong to: both loss terms are
+                              means over it (sga.py:147,150), so every gradient carries 1/n_ref */
+  int32_t operand;         /* sga_operand used by sga_step / sga_grad */
+  float lmbda;             /* --lambda (sga.py:157-163); <= 0 means rate only */
+  float lr, beta1, beta2, adam_eps;   /* adam.py:9-10 ; sga.py:190 uses lr = 0.005 */
+  float clip_eps;          /* epsilon of the atanh clip, 1e-5 (sga.py:30) */
+  uint64_t seed;           /* key of the Philox4x32-10 Gumbel noise stream */
+} sga_config;
+
+/* Weights in the reference's variable layout (float32 device pointers; kernels (kh,kw,Cin,Cout),
+ * gamma (in,out)); index = layer number inside the transform (nn_models.py). */
+typedef struct {
+  const float* ga_kernel[4]; const float* ga_bias[4]; const float* ga_beta[3]; const float* ga_gamma[3];
+  const float* gs_kernel[4]; const float* gs_bias[4]; const float* gs_beta[3]; const float* gs_gamma[3];
+  const float* ha_kernel[3]; const float* ha_bias[2];
+  const float* hs_kernel[3]; const float* hs_bias[3];
+  const float* eb_matrix[4]; const float* eb_bias[4]; const float* eb_factor[3];
+} sga_weights;
+
+typedef struct sga_ctx sga_ctx;
+
+/* stats_out layout (floats): [0] rd_loss [1] train_mse [2] train_bpp, then for image n (0-based):
+ *   [3+5n] psnr  [4+5n] y_bpp  [5+5n] z_bpp  [6+5n] sse (float reconstruction, sum over h,w,c)
+ *   [7+5n] mse of the rounded reconstruction (0..255 scale)                       -> 3 + 5*n_images floats
+ * rd_loss / train_mse / train_bpp are this shard's contribution: sum over local images / n_ref. */
+#define SGA_STATS_HEADER 3
+#define SGA_STATS_PER_IMAGE 5
+
+const char* sga_last_error(void);
+int sga_version(void);
+
+int sga_create(const sga_config* cfg, sga_ctx** out);
+int sga_destroy(sga_ctx* ctx);
+/* bytes of device workspace owned by the context */
+size_t sga_workspace_bytes(const sga_ctx* ctx);
+/* latent shapes: y is [n, hy, wy, C], z is [n, hz, wz, C] */
+int sga_latent_shape(const sga_ctx* ctx, int32_t* hy, int32_t* wy, int32_t* hz, int32_t* wz);
+
+/* Copies / re-lays-out the weights into the context (transposed + bf16 copies for the tcgen05 path). */
+int sga_bind_weights(sga_ctx* ctx, const sga_weights* w, void* stream);
+
+/* y_init = g_a(x), z_init = h_a(y_init)   (sga.py:77-78,207; nn_models.py:5-36,73-103).  Always fp32. */
+int sga_encode_init(sga_ctx* ctx, const float* x, float* y_out, float* z_out, void* stream);
+
+/* One evaluation of the reference's per-iteration graph (sga.py:212-214): gradients of rd_loss w.r.t.
+ * y and z and the scalar statistics.  `step` selects the noise counter; if noise_y/noise_z are non-null
+ * they hold injected uniforms in (0,1), shape [2][numel] (DOWN logits first), and replace the Philox draw. */
+int sga_grad(sga_ctx* ctx, const float* x, const float* y, const float* z, float temperature, int32_t step,
+             const float* noise_y, const float* noise_z, float* grad_y, float* grad_z, float* stats_out,
+             void* stream);
+
+/* sga_grad followed by the Adam update of adam.py:36-57 on y, z (in place) with moments m_*, v_*.
+ * `step` is also adam's `iterations` (0-based). */
+int sga_step(sga_ctx* ctx, const float* x, float* y, float* z, float* m_y, float* v_y, float* m_z, float* v_z,
+             float temperature, int32_t step, const float* noise_y, const float* noise_z, float* stats_out,
+             void* stream);
+
+/* Final evaluation with hard-rounded latents (sga.py:240-247), always fp32: round-half-even of y, z fed as
+ * y_tilde / z_tilde.  stats_out as above (rd_loss etc. computed on the rounded latents). */
+int sga_eval_hard(sga_ctx* ctx, const float* x, const float* y, const float* z, float* stats_out, void* stream);
+
+/* ---- operator-level entry points (used by the parity tests; same kernels the step uses) -------------- */
+
+/* a2: Gumbel soft rounding (sga.py:88-98,111-121).  u = [2][numel] uniforms or NULL -> Philox(seed, step, tensor_id). */
+int sga_op_soft_round(const float* v, const float* u, int64_t numel, float temperature, float clip_eps,
+                      uint64_t seed, int32_t step, int32_t tensor_id, float* v_tilde, float* dvt_dv, void* stream);
+/* a3: factorised-prior likelihood (tfc EntropyBottleneck._likelihood; learned_prior.py:78-121,296-347).
+ * params: matrix_i/bias_i/factor_i device pointers in the reference layout. p_out and dp_out may be NULL. */
+int sga_op_eb_likelihood(const float* z_tilde, int64_t numel, int32_t channels, const float* const matrix[4],
+                         const float* const bias[4], const float* const factor[3], float* p_out, float* dp_out,
+                         void* stream);
+/* a6: box-convolved Gaussian likelihood (utils.py:80-102) with scale bound 0.11 and its partials. */
+int sga_op_gauss_likelihood(const float* y_tilde, const float* mu, const float* log_sigma, int64_t numel,
+                            float* p_out, float* dp_dy, float* dp_dsigma_bounded, void* stream);
+/* a12: Adam (adam.py:36-57), float32 state, lr_t computed on the host in double. */
+int sga_op_adam(float* p, float* m, float* v, const float* g, int64_t numel, float lr, float beta1, float beta2,
+                float eps, int32_t iterations, void* stream);
+/* a4/a7/a14: one (de)conv of nn_models.py. kind: 0 = up2 (corr=False, strides_up=2), 1 = dgrad of up2,
+ * 2 = stride-1 true conv (corr=False), 3 = dgrad of 2, 4 = corr stride 2 (strides_down=2), 5 = corr stride 1.
+ * kernel (kh,kw,Cin,Cout) in the reference layout; x [n,h,w,cin_of_op]; out [n,ho,wo,cout_of_op];
+ * bias may be NULL; relu != 0 applies ReLU.  operand selects fp32 SIMT or bf16 tcgen05. */
+int sga_op_conv(int32_t kind, int32_t operand, const float* x, const float* kernel, const float* bias,
+                int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t relu,
+                float* out, void* stream);
+/* IGDN forward (x*sqrt(beta + x^2 @ gamma)) and its backward; inverse = 0 gives forward GDN (x*rsqrt). */
+int sga_op_gdn(int32_t operand, int32_t inverse, const float* x, const float* beta, const float* gamma,
+               int64_t pixels, int32_t channels, float* out, float* s_out, void* stream);
+int sga_op_igdn_bwd(int32_t operand, const float* g, const float* x, const float* s, const float* gamma,
+                    int64_t pixels, int32_t channels, float* gx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGA_B200_H_ */

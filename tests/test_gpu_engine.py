@@ -1,0 +1,117 @@
+"""End-to-end parity of the SGA step (C ABI: sga_encode_init / sga_grad / sga_step / sga_eval_hard) against the
+CPU oracle with identical Philox noise, and against the committed golden fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sga_oracle as O
+from helpers import make_case, rel_err, rms_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(W, n, h, w, C, lmbda, operand, seed=0, n_ref=None):
+    from sga_b200.engine import SgaEngine
+    return SgaEngine(W, n, h, w, C, lmbda, n_ref=n_ref, operand=operand, seed=seed)
+
+
+@pytest.mark.parametrize("C,n,h,w", [(16, 2, 48, 32), (32, 1, 40, 56), (16, 1, 75, 50)])
+def test_encode_init_f32(C, n, h, w):
+    """a14: y_init, z_init (sga.py:207) incl. odd sizes (ceil division at every stride-2 stage)."""
+    W, Wt, x, _, _ = make_case(C, n, h, w)
+    y_o, z_o = O.analysis(x, Wt)
+    eng = _engine(W, n, h, w, C, 0.01, "f32")
+    y, z = eng.encode_init(x.cuda())
+    assert tuple(y.shape) == tuple(y_o.shape) and tuple(z.shape) == tuple(z_o.shape)
+    assert rel_err(y, y_o) < 2e-5 and rel_err(z, z_o) < 2e-5
+
+
+@pytest.mark.parametrize("C,n,h,w,T,lmbda", [(16, 2, 48, 32, 0.5, 0.01), (32, 1, 64, 64, 0.2, 0.08), (16, 1, 75, 50, 0.5, 0.01),
+                                             (16, 2, 32, 32, 0.3, 0.0)])
+def test_grad_f32(C, n, h, w, T, lmbda):
+    """The per-iteration sess.run of sga.py:212-214 in float32: gradients and statistics."""
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=C)
+    step, seed = 3, 77
+    ref = O.sga_graph(x, y, z, Wt, T, O.draw_noise(y, z, seed, step), lmbda)
+    eng = _engine(W, n, h, w, C, lmbda, "f32", seed=seed)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), T, step)
+    s = eng.unpack_stats(stats.cpu().numpy())
+    assert abs(s["rd_loss"] - float(ref["rd_loss"])) <= 2e-5 * abs(float(ref["rd_loss"]))
+    assert abs(s["train_mse"] - float(ref["train_mse"])) <= 2e-5 * abs(float(ref["train_mse"]))
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-5 * abs(float(ref["train_bpp"]))
+    assert np.abs(s["psnr"] - ref["psnr"].numpy()).max() < 1e-3
+    assert rel_err(gy, ref["grad_y"]) < 2e-4 and rel_err(gz, ref["grad_z"]) < 2e-4
+
+
+def test_grad_f32_injected_noise_and_nref():
+    """noise_or_null path and the 1/n_ref gradient scale of a shard (SURVEY 8e parity trap)."""
+    C, n, h, w = 16, 1, 32, 48
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=9)
+    g = torch.Generator().manual_seed(5)
+    uy = torch.rand((2,) + tuple(y.shape), generator=g).clamp(1e-6, 1 - 1e-6)
+    uz = torch.rand((2,) + tuple(z.shape), generator=g).clamp(1e-6, 1 - 1e-6)
+    ref = O.sga_graph(x, y, z, Wt, 0.4, (uy[0], uy[1], uz[0], uz[1]), 0.01, n_ref=24)
+    eng = _engine(W, n, h, w, C, 0.01, "f32", n_ref=24)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.4, 0, uy.contiguous().cuda(), uz.contiguous().cuda())
+    assert rel_err(gy, ref["grad_y"]) < 2e-4 and rel_err(gz, ref["grad_z"]) < 2e-4
+    assert abs(float(stats[0]) - float(ref["rd_loss"])) <= 2e-5 * abs(float(ref["rd_loss"]))
+
+
+def test_golden_fixture_f32():
+    """Full loop (init -> 4 steps -> hard eval) against tests/golden/sga_c16.npz (made by make_golden.py)."""
+    import sga_b200
+    from sga_b200.schedule import annealed_temperature
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "sga_c16.npz"))
+    C, n, h, w, its, seed = (int(gold[k]) for k in ("C", "n", "h", "w", "its", "seed"))
+    lmbda = float(gold["lmbda"])
+    W = sga_b200.weights.make_synthetic(C, seed)
+    x = torch.from_numpy(sga_b200.synth.synthetic_images(n, h, w, seed).astype(np.float32) / 255.0).cuda()
+    eng = _engine(W, n, h, w, C, lmbda, "f32", seed=seed)
+    y, z = eng.encode_init(x)
+    gy, gz, _ = eng.grad(x, y, z, float(gold["T"][0]), 0)
+    assert rel_err(gy, gold["grad_y0"]) < 2e-4 and rel_err(gz, gold["grad_z0"]) < 2e-4
+    st = eng.new_state(y, z)
+    for it in range(its):
+        T = annealed_temperature(it, r=float(gold["annealing_rate"]), ub=0.5, scheme="exp0", t0=int(gold["t0"]))
+        assert abs(T - float(gold["T"][it])) < 1e-12
+        eng.step(x, st, T, it)
+        s = eng.unpack_stats(eng.stats.cpu().numpy())
+        assert abs(s["rd_loss"] - gold["rd_loss"][it]) <= 1e-4 * abs(gold["rd_loss"][it])
+        assert np.abs(s["psnr"] - gold["psnr"][it]).max() < 2e-3
+    assert (st["y"].cpu().numpy() - gold["y_final"]).__abs__().max() < 2e-4
+    ev = eng.eval_hard(x, st["y"], st["z"])
+    assert np.abs(ev["est_bpp"] - gold["eval_est_bpp"]).max() < 1e-3          # north_star tolerance: 1e-3 bpp
+    assert np.abs(ev["psnr"] - gold["eval_psnr"]).max() < 0.01                # north_star tolerance: 0.01 dB
+
+
+@pytest.mark.parametrize("C,n,h,w", [(64, 1, 64, 64), (64, 2, 96, 64), (192, 1, 128, 96)])
+def test_grad_bf16_vs_oracle(C, n, h, w):
+    """bf16 tcgen05 path of the whole graph vs the float32 oracle: statistics to 1e-3 relative, gradients to bf16
+    accumulation accuracy (operands carry 8 mantissa bits through 4 (de)conv + IGDN stages and back)."""
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=C + 1)
+    step, seed, T, lmbda = 11, 3, 0.35, 0.01
+    ref = O.sga_graph(x, y, z, Wt, T, O.draw_noise(y, z, seed, step), lmbda)
+    eng = _engine(W, n, h, w, C, lmbda, "bf16", seed=seed)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), T, step)
+    s = eng.unpack_stats(stats.cpu().numpy())
+    assert torch.isfinite(gy).all() and torch.isfinite(gz).all()
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-3 * abs(float(ref["train_bpp"]))
+    assert abs(s["train_mse"] - float(ref["train_mse"])) <= 5e-3 * abs(float(ref["train_mse"]))
+    assert np.abs(s["psnr"] - ref["psnr"].numpy()).max() < 0.05
+    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2, rms_rel_err(gy, ref["grad_y"])
+    assert rms_rel_err(gz, ref["grad_z"]) < 3e-2, rms_rel_err(gz, ref["grad_z"])
+
+
+def test_loop_bf16_matches_f32_loop():
+    """20 SGA steps: bf16 loop + fp32 final eval vs the all-fp32 loop on the device (same noise)."""
+    C, n, h, w, its = 64, 1, 96, 96, 20
+    W, Wt, x, _, _ = make_case(C, n, h, w, seed=4)
+    res = {}
+    for operand in ("f32", "bf16"):
+        eng = _engine(W, n, h, w, C, 0.01, operand, seed=1)
+        y, z, ev = eng.run(x.cuda(), its=its, annealing_rate=0.05, t0=5)
+        res[operand] = ev
+    assert np.abs(res["bf16"]["est_bpp"] - res["f32"]["est_bpp"]).max() < 5e-3 * res["f32"]["est_bpp"].max()
+    assert np.abs(res["bf16"]["psnr"] - res["f32"]["psnr"]).max() < 0.05
