@@ -34,11 +34,16 @@ OPERAND_F32 = 0
 OPERAND_BF16 = 1
 STATS_HEADER = 3
 STATS_PER_IMAGE = 5
+PROF_LABELS = 24
+PROF_NAMES = {0: "elementwise", 1: "igdn_fwd", 2: "igdn_bwd", 3: "l3_fwd", 4: "l3_dgrad",
+              8: "hs0_fwd", 9: "hs1_fwd", 10: "hs2_fwd", 11: "hs0_dgrad", 12: "hs1_dgrad", 13: "hs2_dgrad",
+              16: "gs0_fwd", 17: "gs1_fwd", 18: "gs2_fwd", 19: "gs0_dgrad", 20: "gs1_dgrad", 21: "gs2_dgrad"}
 
 # every symbol include/sga_b200.h declares
 EXPORTS = [
     "sga_last_error", "sga_version", "sga_create", "sga_destroy", "sga_workspace_bytes", "sga_latent_shape",
-    "sga_bind_weights", "sga_encode_init", "sga_grad", "sga_step", "sga_eval_hard", "sga_op_soft_round",
+    "sga_bind_weights", "sga_encode_init", "sga_grad", "sga_step", "sga_eval_hard", "sga_reconstruction",
+    "sga_launch_count", "sga_profile_enable", "sga_profile_read", "sga_op_soft_round",
     "sga_op_eb_likelihood", "sga_op_gauss_likelihood", "sga_op_adam", "sga_op_conv", "sga_op_gdn", "sga_op_igdn_bwd",
 ]
 
@@ -72,6 +77,11 @@ def load():
     lib.sga_grad.argtypes = [vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     lib.sga_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp]
     lib.sga_eval_hard.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.sga_reconstruction.argtypes = [vp, vp, vp]
+    lib.sga_launch_count.restype = ctypes.c_longlong
+    lib.sga_launch_count.argtypes = []
+    lib.sga_profile_enable.argtypes = [vp, i32]
+    lib.sga_profile_read.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32), i32]
     lib.sga_op_soft_round.argtypes = [vp, vp, i64, f32, f32, u64, i32, i32, vp, vp, vp]
     lib.sga_op_eb_likelihood.argtypes = [vp, i64, i32, vp * 4, vp * 4, vp * 3, vp, vp, vp]
     lib.sga_op_gauss_likelihood.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
@@ -80,7 +90,7 @@ def load():
     lib.sga_op_gdn.argtypes = [i32, i32, vp, vp, vp, i64, i32, vp, vp, vp]
     lib.sga_op_igdn_bwd.argtypes = [i32, vp, vp, vp, vp, i64, i32, vp, vp]
     for name in EXPORTS:
-        if name not in ("sga_last_error", "sga_workspace_bytes"):
+        if name not in ("sga_last_error", "sga_workspace_bytes", "sga_launch_count"):
             getattr(lib, name).restype = ctypes.c_int
     _lib = lib
     return lib

@@ -1,0 +1,135 @@
+"""The `compress` command of the reference's sga.py, on the B200 engine.
+
+Same flags (tf_boilerplate.parse_args, tf_boilerplate.py:91-204), same checkpoint directory layout
+(<checkpoint_dir>/<runname>/, sga.py:180-182), same progress lines (sga.py:226-233), same output file
+rd-sga-lmbda=%g+<runname>-input=<file>.npz with the 7 per-image fields (sga.py:183, 258-269) and the
+`Avg <field>` summary (sga.py:293-295).  Deviation, documented: --sga_its is honoured (the reference parses it but
+hard-codes 2000, sga.py:191-192)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+SCRIPT_NAME = "sga"
+
+
+def parse_args(argv):
+    try:
+        from absl.flags import argparse_flags
+        parser = argparse_flags.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    except Exception:  # absl is optional
+        parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--verbose", "-V", action="store_true",
+                        help="Report bitrate and distortion when training or compressing.")
+    parser.add_argument("--num_filters", type=int, default=-1, help="Number of filters in the latents.")
+    parser.add_argument("--num_hfilters", type=int, default=-1, help="Number of filters in the hyper latents.")
+    parser.add_argument("--checkpoint_dir", default="./checkpoints", help="Directory where to save/load model checkpoints.")
+    sub = parser.add_subparsers(title="commands", dest="command", help="Only 'compress' is supported (sga.py:303).")
+    c = sub.add_parser("compress", formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                       description="Runs SGA iterative inference on an image or a .npy batch and writes RD statistics.")
+    c.add_argument("--results_dir", default="./results", help="Directory for storing compression stats/results.")
+    c.add_argument("--lambda", type=float, default=-1, dest="lmbda", help="Lambda for rate-distortion tradeoff.")
+    c.add_argument("--sga_its", type=int, default=2000, help="Number of SGA iterations.")
+    c.add_argument("--annealing_rate", type=float, default=1e-3, help="Annealing rate for SGA.")
+    c.add_argument("--t0", type=int, default=700, help="Number of 'soft-quantization' iterations before annealing.")
+    c.add_argument("--operand", choices=["bf16", "f32"], default="bf16",
+                   help="(new) arithmetic of the (de)conv stacks inside the loop; init and final eval are always f32.")
+    c.add_argument("runname", help="Model name identifier, like 'mbt2018-num_filters=192-lmbda=0.01'")
+    c.add_argument("input_file", help="Input filename (image, or .npy uint8 [N,H,W,3]).")
+    c.add_argument("output_file", nargs="?", help="Output filename (optional, unused by sga.py).")
+    args = parser.parse_args(argv[1:])
+    if args.command is None:
+        parser.print_usage()
+        sys.exit(2)
+    return args
+
+
+def load_input(path):
+    if path.endswith(".npy"):
+        X = np.load(path)                                     # sga.py:41-43
+    else:
+        from PIL import Image
+        X = np.asarray(Image.open(path).convert("RGB"))[None, ...]    # sga.py:45-48
+    if X.ndim != 4 or X.shape[-1] != 3:
+        raise ValueError("expected images of shape [N,H,W,3], got %s" % (X.shape,))
+    return X
+
+
+def compress(args, out=print):
+    import torch
+    from . import dist as D
+    from . import weights as Wm
+    from .engine import EVAL_FIELDS, SgaEngine
+    from .msssim import msssim_per_image
+
+    rank, ws, local = D.init_process_group()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    say = out if rank == 0 else (lambda *a, **k: None)
+    X = load_input(args.input_file)
+    num_images, H, Wd = int(X.shape[0]), int(X.shape[1]), int(X.shape[2])
+    if args.lmbda < 0:                                        # sga.py:157-159
+        args.lmbda = float(args.runname.split("lmbda=")[1].split("-")[0])
+        say("Defaulting lmbda (mse coefficient) to %g as used in model training." % args.lmbda)
+    W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, args.num_filters)
+    results = {k: [] for k in EVAL_FIELDS}
+    engines = {}
+    for (b_lo, b_hi) in D.reference_batches(num_images, H * Wd):
+        n_ref = b_hi - b_lo
+        lo, hi = D.shard_range(n_ref, rank, ws)
+        n_loc = hi - lo
+        say("----RD Optimization----")                        # sga.py:206
+        rows = np.zeros((0, 7), dtype=np.float32)
+        eng = None
+        if n_loc > 0:
+            if n_loc not in engines or engines[n_loc][1] != n_ref:
+                if n_loc in engines:
+                    engines[n_loc][0].close()
+                engines[n_loc] = (SgaEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref,
+                                            operand=args.operand, seed=0), n_ref)
+            eng = engines[n_loc][0]
+            x = torch.from_numpy(X[b_lo + lo:b_lo + hi].astype(np.float32) / 255.0).cuda()       # sga.py:52-53
+        def log(it, T, s, extra):
+            tot = D.allreduce_scalars([s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())]
+                                      + ([extra["rd_loss"], extra["train_bpp"], float(extra["psnr"].sum())] if extra else []))
+            line = "it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (it, T, tot[0], tot[1], tot[2], tot[3] / n_ref)
+            if extra:                                         # sga.py:218-230 (--verbose)
+                line += "\t after rounding: rd_loss=%.4f, bpp=%.4f psnr=%.4f" % (tot[4], tot[5], tot[6] / n_ref)
+            say(line)
+        if eng is not None:
+            y, z, ev = eng.run(x, its=args.sga_its, annealing_rate=args.annealing_rate, t0=args.t0, log=log,
+                               verbose=args.verbose)
+            ms = msssim_per_image(eng.reconstruction(), x)
+            rows = np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
+                             ev["est_y_bpp"], ev["est_z_bpp"]], axis=1).astype(np.float32)
+        elif ws > 1:
+            # ranks without images still take part in the log-point all-reduces
+            from .schedule import annealed_temperature
+            for it in range(args.sga_its):
+                if it % 100 == 0 or it + 1 == args.sga_its:
+                    D.allreduce_scalars([0.0] * (7 if args.verbose else 4))
+        say()
+        full = D.gather_rows(rows, n_ref, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
+        for i, k in enumerate(EVAL_FIELDS):
+            results[k] += full[:, i].tolist()
+    for e, _ in engines.values():
+        e.close()
+    if rank != 0:
+        return None
+    results = {k: np.asarray(v) for k, v in results.items()}
+    input_file = os.path.basename(args.input_file)
+    trained_script_name = args.runname.split("-")[0]
+    save_file = "rd-%s-input=%s.npz" % (args.runname, input_file)
+    if SCRIPT_NAME != trained_script_name:                    # sga.py:263-268
+        save_file = "rd-%s-lmbda=%g+%s-input=%s.npz" % (SCRIPT_NAME, args.lmbda, args.runname, input_file)
+    np.savez(os.path.join(args.results_dir, save_file), **results)
+    for k in EVAL_FIELDS:
+        say("Avg {}: {:0.4f}".format(k, results[k].mean()))   # sga.py:293-295
+    return results
+
+
+def main(argv=None):
+    args = parse_args(sys.argv if argv is None else argv)
+    assert args.command == "compress", "Only compression is supported."     # sga.py:303
+    compress(args)

@@ -10,6 +10,7 @@
 namespace sga {
 
 static thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -68,6 +69,16 @@ struct sga_ctx {
   IgdnTc *ig_f[3] = {0, 0, 0}, *ig_b[3] = {0, 0, 0};
   L3Tc* l3 = nullptr;
 
+  // event-based per-kernel timing (sga_profile_*)
+  bool prof = false;
+  struct ProfRec { int label; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+
   template <typename T>
   int alloc(T** p, long long count) {
     if (count <= 0) count = 1;
@@ -86,6 +97,21 @@ struct sga_ctx {
 };
 
 namespace sga {
+
+// run `expr` (one launch group) bracketed by events when profiling is on
+#define PROF(c, label, st, expr)                                           \
+  do {                                                                     \
+    if ((c)->prof && (c)->prof_recs.size() < 16384) {                      \
+      sga_ctx::ProfRec _r{(label), (c)->prof_event(), (c)->prof_event()};  \
+      cudaEventRecord(_r.a, (st));                                         \
+      int _s = (expr);                                                     \
+      cudaEventRecord(_r.b, (st));                                         \
+      (c)->prof_recs.push_back(_r);                                        \
+      if (_s != SGA_OK) return _s;                                         \
+    } else {                                                               \
+      SGA_TRY(expr);                                                       \
+    }                                                                      \
+  } while (0)
 
 static void compute_dims(const sga_config& c, Dims& d) {
   d.N = c.n_images; d.H = c.height; d.W = c.width; d.C = c.num_filters;
@@ -231,37 +257,37 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   const sga_config& g = c->cfg;
   const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
   SGA_CUDA(cudaMemsetAsync(c->acc, 0, 4 * d.N * sizeof(double), st));
-  SGA_TRY(launch_z_path<bf16>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, 0, rate_scale,
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_z_path<bf16>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, 0, rate_scale,
                               c->b_zt, c->gz_rate, c->dz, c->acc + d.N, st));
-  SGA_TRY(tc_conv_launch(c->tc_hs[0], c->hs[0].bias, 1, nullptr, c->b_h0, nullptr, st));
-  SGA_TRY(tc_conv_launch(c->tc_hs[1], c->hs[1].bias, 1, nullptr, c->b_h1, nullptr, st));
-  SGA_TRY(tc_conv_launch(c->tc_hs[2], c->hs[2].bias, 0, nullptr, nullptr, c->h2, st));
-  SGA_TRY(launch_y_path<bf16>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, 0,
+  PROF(c, SGA_PROF_CONV_HS + 0, st, tc_conv_launch(c->tc_hs[0], c->hs[0].bias, 1, nullptr, c->b_h0, nullptr, st));
+  PROF(c, SGA_PROF_CONV_HS + 1, st, tc_conv_launch(c->tc_hs[1], c->hs[1].bias, 1, nullptr, c->b_h1, nullptr, st));
+  PROF(c, SGA_PROF_CONV_HS + 2, st, tc_conv_launch(c->tc_hs[2], c->hs[2].bias, 0, nullptr, nullptr, c->h2, st));
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_y_path<bf16>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, 0,
                               rate_scale, c->b_yt, c->gy_rate, c->dy, c->b_gh2, c->acc, st));
   for (int i = 0; i < 3; ++i) {
-    SGA_TRY(tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
-    SGA_TRY(igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
+    PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
+    PROF(c, SGA_PROF_IGDN_FWD, st, igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
   }
   const float grad_scale =
       (g.lmbda > 0.0f) ? static_cast<float>(2.0 * 65025.0 * g.lmbda / (static_cast<double>(g.n_ref) * d.H * d.W * 3.0))
                        : 0.0f;
-  SGA_TRY(l3_tc_forward(c->l3, c->gs3_bias_host, x, grad_scale, nullptr, c->b_gx4, c->acc + 2 * d.N, c->acc + 3 * d.N,
+  PROF(c, SGA_PROF_L3_FWD, st, l3_tc_forward(c->l3, c->gs3_bias_host, x, grad_scale, nullptr, c->b_gx4, c->acc + 2 * d.N, c->acc + 3 * d.N,
                         st));
-  if (stats) SGA_TRY(launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
+  if (stats) PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
   // ---- backward
   if (g.lmbda > 0.0f) {
-    SGA_TRY(l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
+    PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
     for (int i = 2; i >= 0; --i) {
-      SGA_TRY(igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
-      if (i == 0) SGA_TRY(tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
-      else SGA_TRY(tc_conv_launch(c->tc_gs_d[i], nullptr, 0, nullptr, c->b_ga[i - 1], nullptr, st));
+      PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
+      if (i == 0) PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
+      else PROF(c, SGA_PROF_CONV_GS + 3 + i, st, tc_conv_launch(c->tc_gs_d[i], nullptr, 0, nullptr, c->b_ga[i - 1], nullptr, st));
     }
   } else {
     SGA_CUDA(cudaMemsetAsync(c->gy_dist, 0, d.ny * sizeof(float), st));
   }
-  SGA_TRY(tc_conv_launch(c->tc_hs_d[2], nullptr, 0, c->b_h1, c->b_gh1, nullptr, st));
-  SGA_TRY(tc_conv_launch(c->tc_hs_d[1], nullptr, 0, c->b_h0, c->b_gh0, nullptr, st));
-  SGA_TRY(tc_conv_launch(c->tc_hs_d[0], nullptr, 0, nullptr, nullptr, c->gz_hyper, st));
+  PROF(c, SGA_PROF_CONV_HS + 5, st, tc_conv_launch(c->tc_hs_d[2], nullptr, 0, c->b_h1, c->b_gh1, nullptr, st));
+  PROF(c, SGA_PROF_CONV_HS + 4, st, tc_conv_launch(c->tc_hs_d[1], nullptr, 0, c->b_h0, c->b_gh0, nullptr, st));
+  PROF(c, SGA_PROF_CONV_HS + 3, st, tc_conv_launch(c->tc_hs_d[0], nullptr, 0, nullptr, nullptr, c->gz_hyper, st));
   return SGA_OK;
 }
 
@@ -342,6 +368,8 @@ int sga_destroy(sga_ctx* c) {
     igdn_tc_destroy(c->ig_f[i]); igdn_tc_destroy(c->ig_b[i]);
   }
   l3_tc_destroy(c->l3);
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
   return SGA_OK;
@@ -457,16 +485,53 @@ int sga_step(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SGA_TRY(grad_common(c, x, y, z, T, step, ny, nz, stats, st));
   const sga_config& g = c->cfg;
-  SGA_TRY(launch_adam(y, m_y, v_y, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1, g.beta2, g.adam_eps, step,
-                      nullptr, st));
-  SGA_TRY(launch_adam(z, m_z, v_z, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1, g.beta2, g.adam_eps, step,
-                      nullptr, st));
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_adam(y, m_y, v_y, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1,
+                                                g.beta2, g.adam_eps, step, nullptr, st));
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_adam(z, m_z, v_z, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1,
+                                                g.beta2, g.adam_eps, step, nullptr, st));
   return SGA_OK;
 }
 
 int sga_eval_hard(sga_ctx* c, const float* x, const float* y, const float* z, float* stats, void* stream) {
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
   return forward_f32(c, x, y, z, 1.0f, 0, nullptr, nullptr, 1, false, stats, static_cast<cudaStream_t>(stream));
+}
+
+int sga_reconstruction(sga_ctx* c, float* xt_out, void* stream) {
+  SGA_CHECK(c && c->bound && xt_out, "bad argument");
+  const Dims& d = c->d;
+  // crop [n, Hs4, Ws4, 3] -> [n, H, W, 3]  (sga.py:123)
+  for (int n = 0; n < d.N; ++n)
+    SGA_CUDA(cudaMemcpy2DAsync(xt_out + static_cast<size_t>(n) * d.H * d.W * 3, static_cast<size_t>(d.W) * 3 * sizeof(float),
+                               c->f_xt + static_cast<size_t>(n) * d.Hs[4] * d.Ws[4] * 3,
+                               static_cast<size_t>(d.Ws[4]) * 3 * sizeof(float), static_cast<size_t>(d.W) * 3 * sizeof(float),
+                               d.H, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return SGA_OK;
+}
+
+long long sga_launch_count(void) { return sga::g_launches; }
+
+int sga_profile_enable(sga_ctx* c, int32_t enable) {
+  SGA_CHECK(c != nullptr, "null context");
+  c->prof = enable != 0;
+  return SGA_OK;
+}
+
+int sga_profile_read(sga_ctx* c, float* ms, int32_t* count, int32_t n_labels) {
+  SGA_CHECK(c != nullptr && ms != nullptr, "null argument");
+  for (auto& r : c->prof_recs) {
+    SGA_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.0f;
+    SGA_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.label >= 0 && r.label < n_labels) {
+      ms[r.label] += t;
+      if (count) count[r.label] += 1;
+    }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  return SGA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -35,7 +35,12 @@ void set_error(const char* fmt, ...);
     if (_s != SGA_OK) return _s; \
   } while (0)
 
-#define SGA_LAUNCH_CHECK() SGA_CUDA(cudaGetLastError())
+extern thread_local long long g_launches;   // kernels launched by this library (sga_launch_count)
+#define SGA_LAUNCH_CHECK()        \
+  do {                            \
+    ++sga::g_launches;            \
+    SGA_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // A strided NHWC view (channel stride 1). Phase views of a [N,2H,2W,C] tensor use sH = 2*(2W)*C, sW = 2*C.
 struct View {

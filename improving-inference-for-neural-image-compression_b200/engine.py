@@ -121,6 +121,26 @@ class SgaEngine:
         _lib.check(self.lib.sga_eval_hard(self.ctx, _ptr(x), _ptr(y), _ptr(z), _ptr(self.stats), _stream()))
         return self.unpack_stats(self.stats.cpu().numpy())
 
+    def reconstruction(self):
+        """x_tilde [n,H,W,3] (float, un-clipped) of the most recent fp32 forward (e.g. eval_hard)."""
+        xt = torch.empty((self.n, self.h, self.w, 3), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.sga_reconstruction(self.ctx, _ptr(xt), _stream()))
+        return xt
+
+    def profile(self, enable):
+        _lib.check(self.lib.sga_profile_enable(self.ctx, int(bool(enable))))
+
+    def profile_read(self):
+        """{label name: (milliseconds, launch groups)} accumulated since the last read."""
+        ms = (ctypes.c_float * _lib.PROF_LABELS)()
+        cnt = (ctypes.c_int32 * _lib.PROF_LABELS)()
+        _lib.check(self.lib.sga_profile_read(self.ctx, ms, cnt, _lib.PROF_LABELS))
+        return {_lib.PROF_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(_lib.PROF_LABELS)
+                if i in _lib.PROF_NAMES and cnt[i] > 0}
+
+    def launch_count(self):
+        return int(self.lib.sga_launch_count())
+
     def unpack_stats(self, s):
         per = s[_lib.STATS_HEADER:].reshape(self.n, _lib.STATS_PER_IMAGE)
         return dict(rd_loss=float(s[0]), train_mse=float(s[1]), train_bpp=float(s[2]), psnr=per[:, 0].copy(),

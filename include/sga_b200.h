@@ -105,6 +105,27 @@ int sga_step(sga_ctx* ctx, const float* x, float* y, float* z, float* m_y, float
  * y_tilde / z_tilde.  stats_out as above (rd_loss etc. computed on the rounded latents). */
 int sga_eval_hard(sga_ctx* ctx, const float* x, const float* y, const float* z, float* stats_out, void* stream);
 
+/* Copies the cropped reconstruction x_tilde [n,H,W,3] (float, un-clipped) of the most recent fp32 forward
+ * (sga_eval_hard, or sga_grad/sga_step with operand f32) -- used for MS-SSIM (sga.py:175) and PNG dumps. */
+int sga_reconstruction(sga_ctx* ctx, float* xt_out, void* stream);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------
+ * sga_launch_count: kernels launched by this library in the calling thread since load.
+ * sga_profile_enable(ctx, 1): bracket every launch group of sga_grad/sga_step with CUDA events on the launching
+ * stream; sga_profile_read synchronises the recorded events, adds the elapsed milliseconds into ms[label] and the
+ * number of groups into count[label] (label < n_labels, see SGA_PROF_*), and clears the record. */
+#define SGA_PROF_ELEMENTWISE 0
+#define SGA_PROF_IGDN_FWD 1
+#define SGA_PROF_IGDN_BWD 2
+#define SGA_PROF_L3_FWD 3
+#define SGA_PROF_L3_DGRAD 4
+#define SGA_PROF_CONV_HS 8      /* +0..2 forward layer i, +3..5 dgrad of layer i */
+#define SGA_PROF_CONV_GS 16     /* +0..2 forward layer i, +3..5 dgrad of layer i */
+#define SGA_PROF_LABELS 24
+long long sga_launch_count(void);
+int sga_profile_enable(sga_ctx* ctx, int32_t enable);
+int sga_profile_read(sga_ctx* ctx, float* ms, int32_t* count, int32_t n_labels);
+
 /* ---- operator-level entry points (used by the parity tests; same kernels the step uses) -------------- */
 
 /* a2: Gumbel soft rounding (sga.py:88-98,111-121).  u = [2][numel] uniforms or NULL -> Philox(seed, step, tensor_id). */

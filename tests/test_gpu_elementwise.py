@@ -28,8 +28,9 @@ def test_soft_round_philox(numel, T):
     # float32 transcendental chains (atanh/log/exp) differ by a few ulp between libm and CUDA
     assert (vt.cpu() - vt_o).abs().max().item() < 2e-5
     assert rel_err(dv, dv_o) < 2e-4
-    ints = v == torch.round(v)
-    assert torch.equal(vt.cpu()[ints], v[ints]) and (dv.cpu()[ints] == 0).all()
+    ints = v == torch.round(v)     # floor == ceil: v_tilde = f*s0 + f*s1 == v up to one rounding, gradient exactly 0
+    assert (vt.cpu()[ints] - v[ints]).abs().max().item() <= 1e-6 * v.abs().max().item()
+    assert (dv.cpu()[ints] == 0).all()
 
 
 def test_soft_round_injected_noise():
@@ -58,10 +59,13 @@ def test_eb_likelihood(C):
     assert rel_err(p, p_o) < 1e-5
     assert rel_err(dp, dp_o) < 1e-4
     # the model is a proper pmf over the integers (size-independent property)
-    ks = torch.arange(-60, 61).float().view(-1, 1).repeat(1, C)
+    # (logistic tails with a scale of ~10: +-3000 covers all but ~1e-4 of the mass)
+    ks = torch.arange(-3000, 3001).float().view(-1, 1).repeat(1, C)
     pk, _ = ops.eb_likelihood(ks.cuda().contiguous(), [eb["matrix_%d" % i].cuda() for i in range(4)],
                               [eb["bias_%d" % i].cuda() for i in range(4)], [eb["factor_%d" % i].cuda() for i in range(3)])
-    assert (pk.sum(0).cpu() - 1).abs().max().item() < 1e-3
+    pk_o, _ = O.eb_likelihood(ks.double(), {k: v.double() for k, v in eb.items()})
+    assert (pk.double().sum(0).cpu() - pk_o.sum(0)).abs().max().item() < 1e-4
+    assert (pk.double().sum(0).cpu() - 1).abs().max().item() < 2e-3
 
 
 def test_gauss_likelihood():

@@ -1,0 +1,144 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute without a GPU),
+weights container, CLI surface, batch segmentation / sharding logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from sga_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sga_b200.h")).read()
+    declared = set(re.findall(r"\b(sga_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sga_status"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sga_version() >= 100
+    assert ctypes.sizeof(_lib.SgaConfig) == 56
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from sga_b200 import SgaError, weights
+    from sga_b200.engine import SgaEngine
+    with pytest.raises(SgaError):
+        SgaEngine(weights.make_synthetic(8, 0), 1, 32, 32, 8, 0.01)
+
+
+def test_argument_errors_are_reported_not_thrown():
+    from sga_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.SgaConfig(n_images=0, height=16, width=16, num_filters=8, n_ref=1, operand=0)
+    ctx = ctypes.c_void_p()
+    assert lib.sga_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1
+    assert b"shape" in lib.sga_last_error()
+    cfg = _lib.SgaConfig(n_images=1, height=16, width=16, num_filters=100, n_ref=1, operand=1)
+    assert lib.sga_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1       # bf16 path needs C % 64 == 0
+    assert lib.sga_destroy(None) == 0
+
+
+def test_weights_layout_and_roundtrip(tmp_path):
+    from sga_b200 import weights
+    W = weights.make_synthetic(16, 1)
+    shapes = weights.variable_shapes(16)
+    assert set(W) == set(shapes)
+    assert shapes["mb_t2018hyper_synthesis_transform/layer_1/kernel"] == (5, 5, 16, 24)      # int(1.5 C)
+    assert shapes["mb_t2018hyper_synthesis_transform/layer_2/kernel"] == (3, 3, 24, 32)
+    assert "hyper_analysis_transform/layer_2/bias" not in shapes                             # nn_models.py:95
+    assert shapes["entropy_bottleneck/matrix_1"] == (16, 3, 3)
+    rn = weights.runname(16, 0.01)
+    assert rn == "mbt2018-num_filters=16-lmbda=0.01"
+    weights.save_checkpoint(str(tmp_path), rn, W)
+    W2 = weights.load_checkpoint(str(tmp_path), rn, 16)
+    assert all(np.array_equal(W[k], W2[k]) for k in W)
+    with pytest.raises(ValueError):
+        weights.load_checkpoint(str(tmp_path), rn, 32)
+    with pytest.raises(FileNotFoundError):
+        weights.load_checkpoint(str(tmp_path), "nope", 16)
+
+
+def test_reparameterised_checkpoint_entries():
+    from sga_b200 import weights
+    rng = np.random.default_rng(0)
+    beta = (1 + rng.random(8)).astype(np.float32)
+    gamma = (0.1 * rng.random((8, 8))).astype(np.float32)
+    raw = {"a/gdn_0/reparam_beta": weights.gdn_to_reparam(beta, weights.GDN_BETA_MIN),
+           "a/gdn_0/reparam_gamma": weights.gdn_to_reparam(gamma, weights.GDN_GAMMA_MIN)}
+    W = weights.deparameterise(raw)
+    assert np.allclose(W["a/gdn_0/beta"], beta, rtol=1e-6) and np.allclose(W["a/gdn_0/gamma"], gamma, atol=1e-7)
+    M = weights.irdft_matrix((5, 5))
+    assert M.shape == (25, 25) and np.allclose(M.T @ M, np.eye(25), atol=1e-9)     # orthonormal basis
+    k = rng.standard_normal((5, 5, 2, 3)).astype(np.float32)
+    rdft = M.T @ k.reshape(25, 6)
+    W = weights.deparameterise({"l/kernel_rdft": rdft, "l/kernel_shape": np.array([5, 5, 2, 3])})
+    assert np.allclose(W["l/kernel"], k, atol=1e-5)
+
+
+def test_cli_surface_matches_reference():
+    """tf_boilerplate.parse_args (tf_boilerplate.py:91-204): same flags, dests and defaults for `compress`."""
+    from sga_b200.cli import parse_args
+    a = parse_args(["sga.py", "--num_filters", "192", "compress", "mbt2018-num_filters=192-lmbda=0.01", "in.npy"])
+    assert a.command == "compress" and a.num_filters == 192 and a.lmbda == -1 and a.sga_its == 2000
+    assert a.annealing_rate == 1e-3 and a.t0 == 700 and a.checkpoint_dir == "./checkpoints" and a.results_dir == "./results"
+    assert a.verbose is False and a.output_file is None and a.num_hfilters == -1
+    a = parse_args(["sga.py", "-V", "--num_filters", "256", "--checkpoint_dir", "/c", "compress", "--lambda", "0.08",
+                    "--sga_its", "10", "--annealing_rate", "2e-3", "--t0", "350", "--results_dir", "/r", "run", "x.png", "o"])
+    assert a.verbose and a.lmbda == 0.08 and a.sga_its == 10 and a.t0 == 350 and a.output_file == "o"
+    with pytest.raises(SystemExit):
+        parse_args(["sga.py"])
+
+
+def test_batch_segmentation_and_shards():
+    """configs.get_eval_batch_size (configs.py:8-9) and the contiguous sharding of each reference batch."""
+    from sga_b200.dist import eval_batch_size, reference_batches, shard_range
+    assert eval_batch_size(768 * 512) == 25 and eval_batch_size(1200 * 1200) == 7 and eval_batch_size(256 * 256) == 153
+    assert reference_batches(24, 768 * 512) == [(0, 24)]
+    b = reference_batches(100, 1200 * 1200)
+    assert b[0] == (0, 7) and b[-1] == (98, 100) and len(b) == 15
+    for n, ws in [(24, 8), (7, 8), (2, 8), (25, 4), (1, 1)]:
+        cover = []
+        for r in range(ws):
+            lo, hi = shard_range(n, r, ws)
+            assert 0 <= lo <= hi <= n
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+    assert [shard_range(24, r, 8) for r in range(8)] == [(3 * r, 3 * r + 3) for r in range(8)]
+
+
+def test_gather_results_gloo_world2(tmp_path):
+    """The only collective of the path (one gather of per-image rows after the loop) on CPU with gloo, world_size 2."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        "sys.path.insert(0, %r)\n"
+        "from sga_b200.dist import gather_rows, shard_range, allreduce_scalars\n"
+        "dist.init_process_group('gloo')\n"
+        "r, ws = dist.get_rank(), dist.get_world_size()\n"
+        "n = 5\n"
+        "lo, hi = shard_range(n, r, ws)\n"
+        "rows = np.stack([np.arange(lo, hi) * 10.0 + k for k in range(5)], axis=1).astype(np.float32)\n"
+        "full = gather_rows(rows, n, r, ws, device='cpu')\n"
+        "tot = allreduce_scalars([float(hi - lo), 1.0], device='cpu')\n"
+        "if r == 0:\n"
+        "    want = np.stack([np.arange(n) * 10.0 + k for k in range(5)], axis=1)\n"
+        "    assert np.array_equal(full, want), full\n"
+        "    assert tot == [5.0, 2.0], tot\n"
+        "    print('GATHER_OK')\n"
+        "dist.destroy_process_group()\n" % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
