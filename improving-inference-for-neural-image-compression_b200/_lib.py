@@ -15,6 +15,7 @@ class SgaConfig(ctypes.Structure):
         ("num_filters", ctypes.c_int32), ("n_ref", ctypes.c_int32), ("operand", ctypes.c_int32),
         ("lmbda", ctypes.c_float), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
         ("adam_eps", ctypes.c_float), ("clip_eps", ctypes.c_float), ("seed", ctypes.c_uint64),
+        ("first_image", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 

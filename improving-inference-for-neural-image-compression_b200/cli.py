@@ -83,11 +83,11 @@ def compress(args, out=print):
         rows = np.zeros((0, 7), dtype=np.float32)
         eng = None
         if n_loc > 0:
-            if n_loc not in engines or engines[n_loc][1] != n_ref:
+            if n_loc not in engines or engines[n_loc][1] != (n_ref, lo):
                 if n_loc in engines:
                     engines[n_loc][0].close()
                 engines[n_loc] = (SgaEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref,
-                                            operand=args.operand, seed=0), n_ref)
+                                            operand=args.operand, seed=0, first_image=lo), (n_ref, lo))
             eng = engines[n_loc][0]
             x = torch.from_numpy(X[b_lo + lo:b_lo + hi].astype(np.float32) / 255.0).cuda()       # sga.py:52-53
         def log(it, T, s, extra):

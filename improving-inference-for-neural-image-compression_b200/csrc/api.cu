@@ -68,6 +68,7 @@ struct sga_ctx {
   TcConv *tc_hs[3] = {0, 0, 0}, *tc_gs[3] = {0, 0, 0}, *tc_hs_d[3] = {0, 0, 0}, *tc_gs_d[3] = {0, 0, 0};
   IgdnTc *ig_f[3] = {0, 0, 0}, *ig_b[3] = {0, 0, 0};
   L3Tc* l3 = nullptr;
+  bool fused = false;   // IGDN runs inside the (de)conv epilogues (num_filters in {64,128,192})
 
   // event-based per-kernel timing (sga_profile_*)
   bool prof = false;
@@ -186,10 +187,11 @@ static int bind_conv(sga_ctx* c, ConvW& w, const float* kernel, const float* bia
   return SGA_OK;
 }
 
-static int make_tc(int kind, const ConvW& w, int N, int Hin, int Win, const bf16* x, TcConv** out) {
+static int make_tc(int kind, const ConvW& w, int N, int Hin, int Win, const bf16* x, TcConv** out, int fuse = 0,
+                   const bf16* mix_op = nullptr) {
   ConvPlan plan;
   SGA_TRY(make_conv_plan(kind, w.kh, w.kw, N, Hin, Win, w.cin, w.cout, &plan));
-  return tc_conv_create(plan, x, plan.w_transposed ? w.wb_dgrad : w.wb_fwd, out);
+  return tc_conv_create(plan, x, plan.w_transposed ? w.wb_dgrad : w.wb_fwd, fuse, mix_op, out);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -202,13 +204,14 @@ static int forward_f32(sga_ctx* c, const float* x, const float* y, const float* 
   const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
   SGA_CUDA(cudaMemsetAsync(c->acc, 0, 4 * d.N * sizeof(double), st));
   SGA_TRY(launch_z_path<float>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, hard, rate_scale,
-                               c->f_zt, want_grad ? c->gz_rate : nullptr, want_grad ? c->dz : nullptr, c->acc + d.N, st));
+                               c->f_zt, want_grad ? c->gz_rate : nullptr, want_grad ? c->dz : nullptr, c->acc + d.N,
+                               g.first_image * (d.nz / d.N), st));
   SGA_TRY(conv_f32(kUp2, c->hs[0], d.N, d.Hz, d.Wz, c->f_zt, true, 1, nullptr, c->f_h0, st));
   SGA_TRY(conv_f32(kUp2, c->hs[1], d.N, 2 * d.Hz, 2 * d.Wz, c->f_h0, true, 1, nullptr, c->f_h1, st));
   SGA_TRY(conv_f32(kS1True, c->hs[2], d.N, d.Hh, d.Wh, c->f_h1, true, 0, nullptr, c->h2, st));
   SGA_TRY(launch_y_path<float>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, hard,
                                rate_scale, c->f_yt, want_grad ? c->gy_rate : nullptr, want_grad ? c->dy : nullptr,
-                               want_grad ? c->f_gh2 : nullptr, c->acc, st));
+                               want_grad ? c->f_gh2 : nullptr, c->acc, g.first_image * (d.ny / d.N), st));
   const float* in = c->f_yt;
   for (int i = 0; i < 3; ++i) {
     SGA_TRY(conv_f32(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, true, 0, nullptr, c->f_xpre[i], st));
@@ -258,15 +261,20 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
   SGA_CUDA(cudaMemsetAsync(c->acc, 0, 4 * d.N * sizeof(double), st));
   PROF(c, SGA_PROF_ELEMENTWISE, st, launch_z_path<bf16>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, 0, rate_scale,
-                              c->b_zt, c->gz_rate, c->dz, c->acc + d.N, st));
+                              c->b_zt, c->gz_rate, c->dz, c->acc + d.N, g.first_image * (d.nz / d.N), st));
   PROF(c, SGA_PROF_CONV_HS + 0, st, tc_conv_launch(c->tc_hs[0], c->hs[0].bias, 1, nullptr, c->b_h0, nullptr, st));
   PROF(c, SGA_PROF_CONV_HS + 1, st, tc_conv_launch(c->tc_hs[1], c->hs[1].bias, 1, nullptr, c->b_h1, nullptr, st));
   PROF(c, SGA_PROF_CONV_HS + 2, st, tc_conv_launch(c->tc_hs[2], c->hs[2].bias, 0, nullptr, nullptr, c->h2, st));
   PROF(c, SGA_PROF_ELEMENTWISE, st, launch_y_path<bf16>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, 0,
-                              rate_scale, c->b_yt, c->gy_rate, c->dy, c->b_gh2, c->acc, st));
+                              rate_scale, c->b_yt, c->gy_rate, c->dy, c->b_gh2, c->acc, g.first_image * (d.ny / d.N), st));
   for (int i = 0; i < 3; ++i) {
-    PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
-    PROF(c, SGA_PROF_IGDN_FWD, st, igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
+    if (c->fused) {
+      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch_igdn_fwd(c->tc_gs[i], c->gs[i].bias, c->gs_beta[i], c->b_xpre[i],
+                                                                c->b_s[i], c->b_act[i], st));
+    } else {
+      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
+      PROF(c, SGA_PROF_IGDN_FWD, st, igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
+    }
   }
   const float grad_scale =
       (g.lmbda > 0.0f) ? static_cast<float>(2.0 * 65025.0 * g.lmbda / (static_cast<double>(g.n_ref) * d.H * d.W * 3.0))
@@ -277,10 +285,19 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   // ---- backward
   if (g.lmbda > 0.0f) {
     PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
-    for (int i = 2; i >= 0; --i) {
-      PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
-      if (i == 0) PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
-      else PROF(c, SGA_PROF_CONV_GS + 3 + i, st, tc_conv_launch(c->tc_gs_d[i], nullptr, 0, nullptr, c->b_ga[i - 1], nullptr, st));
+    if (c->fused) {
+      // IGDN_2 backward stands alone (its producer is the layer-3 dgrad); IGDN_1 / IGDN_0 backward run in the epilogues
+      // of the dgrad convs that produce their upstream gradients
+      PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_xpre[2], c->b_s[2], c->b_gb[2], st));
+      PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_xpre[1], c->b_s[1], c->b_gb[1], st));
+      PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_xpre[0], c->b_s[0], c->b_gb[0], st));
+      PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
+    } else {
+      for (int i = 2; i >= 0; --i) {
+        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
+        if (i == 0) PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
+        else PROF(c, SGA_PROF_CONV_GS + 3 + i, st, tc_conv_launch(c->tc_gs_d[i], nullptr, 0, nullptr, c->b_ga[i - 1], nullptr, st));
+      }
     }
   } else {
     SGA_CUDA(cudaMemsetAsync(c->gy_dist, 0, d.ny * sizeof(float), st));
@@ -315,6 +332,7 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
   SGA_CHECK(cfg->n_images > 0 && cfg->height > 0 && cfg->width > 0, "bad image shape");
   SGA_CHECK(cfg->num_filters >= 8 && cfg->num_filters % 2 == 0, "num_filters must be even and >= 8");
   SGA_CHECK(cfg->n_ref >= 1, "n_ref must be >= 1");
+  SGA_CHECK(cfg->first_image >= 0, "first_image must be >= 0");
   SGA_CHECK(cfg->operand == SGA_OPERAND_F32 || cfg->operand == SGA_OPERAND_BF16, "unknown operand type");
   if (cfg->operand == SGA_OPERAND_BF16)
     SGA_CHECK(cfg->num_filters % 64 == 0 && cfg->num_filters <= 256,
@@ -428,13 +446,23 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
     SGA_TRY(make_tc(kS1TrueDgrad, c->hs[2], d.N, d.Hh, d.Wh, c->b_gh2, &c->tc_hs_d[2]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[1], d.N, d.Hh, d.Wh, c->b_gh1, &c->tc_hs_d[1]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[0], d.N, 2 * d.Hz, 2 * d.Wz, c->b_gh0, &c->tc_hs_d[0]));
+    c->fused = tc_conv_can_fuse(C);
     for (int i = 0; i < 3; ++i) {
       const bf16* in = (i == 0) ? c->b_yt : c->b_act[i - 1];
-      SGA_TRY(make_tc(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, &c->tc_gs[i]));
-      SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i]));
       const long long pix = static_cast<long long>(d.N) * d.Hs[i + 1] * d.Ws[i + 1];
-      SGA_TRY(igdn_tc_create(c->gs_gamma_tb[i], C, pix, 0, &c->ig_f[i]));
-      SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
+      if (c->fused) {
+        SGA_TRY(make_tc(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, &c->tc_gs[i], 1, c->gs_gamma_tb[i]));
+        // the dgrad of layer i produces the upstream gradient of IGDN_{i-1}
+        if (i > 0) SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i], 2,
+                                   c->gs_gamma_b[i - 1]));
+        else SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i]));
+        if (i == 2) SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
+      } else {
+        SGA_TRY(make_tc(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, &c->tc_gs[i]));
+        SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i]));
+        SGA_TRY(igdn_tc_create(c->gs_gamma_tb[i], C, pix, 0, &c->ig_f[i]));
+        SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
+      }
     }
     SGA_TRY(c->alloc(&c->l3_wscatter, 80 * C)); SGA_TRY(c->alloc(&c->l3_wgather, 80 * C));
     SGA_TRY(l3_pack_weights(c->gs[3].w, C, c->l3_wscatter, c->l3_wgather, st));
@@ -596,7 +624,7 @@ int sga_op_conv(int32_t kind, int32_t operand, const float* x, const float* kern
   TcConv* tcv = nullptr;
   s = launch_f32_to_bf16(x, nin, xb, st);
   if (s == SGA_OK) s = launch_pack_weights_bf16(kernel, kh * kw, cin, cout, plan.w_transposed, wb, st);
-  if (s == SGA_OK) s = tc_conv_create(plan, xb, wb, &tcv);
+  if (s == SGA_OK) s = tc_conv_create(plan, xb, wb, 0, nullptr, &tcv);
   if (s == SGA_OK) s = tc_conv_launch(tcv, bias, relu, nullptr, nullptr, out, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (s == SGA_OK && e != cudaSuccess) { set_error("tcgen05 conv failed: %s", cudaGetErrorString(e)); s = SGA_ERR_CUDA; }

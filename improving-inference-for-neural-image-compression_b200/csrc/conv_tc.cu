@@ -1,4 +1,5 @@
-// conv_tc.cu -- bf16 implicit-GEMM (de)convolution on the sm_100a tensor cores.
+// conv_tc.cu -- bf16 implicit-GEMM (de)convolution on the sm_100a tensor cores, optionally fused with the inverse
+// GDN that follows it in the synthesis transform (forward) or precedes it in the backward pass.
 //
 // Every (de)conv of the synthesis / hyper-synthesis transforms (nn_models.py:39-70, 140-170) and its dgrad is a
 // sum over filter taps of  [128 pixels x Cin] * [Cin x Cout]  products (conv_plan.cu).  Per tap and 64-channel slice
@@ -7,10 +8,21 @@
 //            the box lands in shared memory as a K-major SWIZZLE_128B operand tile (128 rows x 128 B)
 //   B tile : TMA 2-D box {64 ch, BLOCK_N} of the pre-packed K-major weights [tap][Cout][Cin]
 //   MMA    : 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) accumulating in TMEM (fp32)
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 and/or fp32 global stores).  Persistent CTAs (one per SM) walk a
-// static tile list; the TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Persistent CTAs (one per SM); the TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  Tiles are issued in waves of gridDim.x spatial tiles per output phase, so the 4 phases of a transposed
+// conv re-read their (shared) input from L2 instead of HBM and every CTA gets the same mix of 9/6/6/4-tap tiles.
+//
+// Fused IGDN (template FUSE): the CxC channel mixing of tfc.GDN(inverse=True) (nn_models.py:51,55,59) runs as a second
+// GEMM on the finished accumulator tile.
+//   forward  (FUSE=1): x = acc + bias;  s = sqrt(beta + x^2 @ gamma);  out = x*s           (stores x, s, out as bf16)
+//   backward (FUSE=2): g = acc;  t = g*x/s;  u = t @ gamma^T;  g_x = g*s + x*u             (stores g_x as bf16)
+// Epilogue pass 1 reads the accumulator, writes the A operand of the mixing GEMM (x^2 or t, bf16, swizzled K-major) to
+// shared memory and releases the accumulator; the MMA warp slots the mixing MMAs of tile i into the main loop of tile
+// i+1 (two halves of N/2 columns into a third TMEM region; gamma streams through the regular B stages); epilogue pass 2
+// finishes the point-wise math from registers (x resp. g*s are kept packed as bf16) and the mixing result in TMEM.
 #include "kernels.h"
+#include "tc_kernels.h"
 #include "tc_common.cuh"
 
 namespace sga {
@@ -27,9 +39,6 @@ constexpr int kTmemCols = 512;
 struct TcJob {
   int tap_begin, ntaps;
   int Ho, Wo;             // pixel grid of the output view
-  int tiles_h, tiles_w;
-  int tile_begin;         // first global tile index of this job
-  int pad_;
   long long out_off;      // element offset of the output view
   long long oH, oW;       // element strides of the output view
 };
@@ -37,32 +46,43 @@ struct TcJob {
 struct alignas(64) TcParams {
   CUtensorMap amap[kMaxViews];
   CUtensorMap bmap;
+  CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
   TcJob job[4];
   Tap taps[kMaxTaps];
   int njobs, N, K, Nn;
   int block_n, n_tiles_n, kchunks, stages;
-  int TH, TW, total_tiles, relu;
+  int TH, TW, tiles_h, tiles_w;
+  int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
+  int relu;
   long long oN;
   const float* bias;
   const __nv_bfloat16* mask;
   __nv_bfloat16* out_bf16;
   float* out_f32;
+  // fused IGDN
+  const float* beta;            // fwd
+  __nv_bfloat16* xpre_out;      // fwd: x = acc + bias
+  __nv_bfloat16* s_out;         // fwd: sqrt(norm)
+  const __nv_bfloat16* x_in;    // bwd: saved x
+  const __nv_bfloat16* s_in;    // bwd: saved s
 };
 
 struct TileCoord { int job, img, h0, w0, n0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile) {
-  int jb = 0;
-#pragma unroll
-  for (int q = 1; q < 4; ++q)
-    if (q < P.njobs && tile >= P.job[q].tile_begin) jb = q;
-  const TcJob& J = P.job[jb];
-  int t = tile - J.tile_begin;
+// slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G)
+__device__ __forceinline__ bool decode_slot(const TcParams& P, int k, TileCoord& tc_) {
+  const int jb = k % P.njobs;
+  int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+  if (t >= P.n_spatial) return false;
   const int nt = t % P.n_tiles_n; t /= P.n_tiles_n;
-  const int tw = t % J.tiles_w; t /= J.tiles_w;
-  const int th = t % J.tiles_h;
-  const int img = t / J.tiles_h;
-  return TileCoord{jb, img, th * P.TH, tw * P.TW, nt * P.block_n};
+  const int tw = t % P.tiles_w; t /= P.tiles_w;
+  const int th = t % P.tiles_h;
+  const int img = t / P.tiles_h;
+  tc_ = TileCoord{jb, img, th * P.TH, tw * P.TW, nt * P.block_n};
+  return true;
+}
+__device__ __forceinline__ int num_waves(const TcParams& P) {
+  return ((P.n_spatial + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) * P.njobs;
 }
 
 template <int NV>
@@ -103,6 +123,11 @@ __device__ __forceinline__ void epilogue_store(const TcParams& P, const uint32_t
   }
 }
 
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// FUSE: 0 = plain conv epilogue, 1 = + IGDN forward, 2 = + IGDN backward.  NF = Cout of the fused variants.
+template <int FUSE, int NF>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -111,23 +136,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
   const int b_bytes = P.block_n * kBlockK * 2;
   const uint32_t a_base = base;
   const uint32_t b_base = base + P.stages * kABytes;
-  uint8_t* tail = smem + P.stages * (kABytes + b_bytes);
-  float* s_bias = reinterpret_cast<float*>(tail);                       // 512 floats
+  constexpr int kA2Bytes = (FUSE != 0) ? (NF / 64) * kABytes : 0;
+  const uint32_t a2_base = b_base + P.stages * b_bytes;            // fused: A operand of the mixing GEMM
+  uint8_t* a2_ptr = smem + P.stages * (kABytes + b_bytes);
+  uint8_t* tail = a2_ptr + kA2Bytes;
+  float* s_bias = reinterpret_cast<float*>(tail);                  // 512 floats: bias (or beta for the fused fwd: +256)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512 * sizeof(float));
-  // bars: full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
+  // bars: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | a2_full | norm_full | norm_empty
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const uint32_t bar_a2 = bar_tempty + 16;
+  const uint32_t bar_nfull = bar_a2 + 8;
+  const uint32_t bar_nempty = bar_nfull + 8;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kAccStride = (FUSE != 0) ? NF : 256;               // TMEM columns between the two accumulators
+  constexpr int kNormCol = 2 * NF;                                 // fused: mixing result (N/2 columns)
+  constexpr int kNHalf = NF / 2;
 
-  for (int i = threadIdx.x; i < P.Nn && i < 512; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < P.Nn && i < 256; i += blockDim.x) {
+    s_bias[i] = P.bias ? P.bias[i] : 0.0f;
+    if (FUSE == 1) s_bias[256 + i] = P.beta[i];
+  }
+  if (FUSE == 0)
+    for (int i = 256 + threadIdx.x; i < P.Nn && i < 512; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
 
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < kMaxViews; ++v) tma_prefetch_desc(&P.amap[v]);
     tma_prefetch_desc(&P.bmap);
+    if (FUSE != 0) tma_prefetch_desc(&P.gmap);
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -136,6 +176,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, 4);
     }
+    mbar_init(bar_a2, 128);
+    mbar_init(bar_nfull, 1);
+    mbar_init(bar_nempty, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -146,20 +189,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *s_tmem;
-
-  const int ksteps_per_tap = P.kchunks;
+  const int nwaves = num_waves(P);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc_ = decode_tile(P, tile);
+      auto mix_loads = [&](int h) {   // gamma rows [h*N/2, +N/2), all K chunks, through the regular B stages
+        for (int kc = 0; kc < NF / 64; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, kNHalf * 128);
+          tma_load_2d(b_base + stage * b_bytes, &P.gmap, bar_full + 8 * stage, kc * kBlockK, h * kNHalf);
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+      };
+      bool pending = false;           // a finished tile whose mixing GEMM has not been issued yet
+      for (int w = 0; w < nwaves; ++w) {
+        TileCoord tc_;
+        if (!decode_slot(P, w, tc_)) continue;
         const TcJob& J = P.job[tc_.job];
+        const int nk = J.ntaps * P.kchunks;
+        const int ins0 = nk / 2, ins1 = (3 * nk) / 4;
+        int k = 0;
         for (int t = 0; t < J.ntaps; ++t) {
           const Tap tap = P.taps[J.tap_begin + t];
-          for (int kc = 0; kc < ksteps_per_tap; ++kc) {
+          for (int kc = 0; kc < P.kchunks; ++kc, ++k) {
+            if (FUSE != 0 && pending) {
+              if (k == ins0) mix_loads(0);
+              if (k == ins1) mix_loads(1);
+            }
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             mbar_arrive_expect_tx(bar_full + 8 * stage, kABytes + b_bytes);
             tma_load_4d(a_base + stage * kABytes, &P.amap[tap.view], bar_full + 8 * stage, kc * kBlockK,
@@ -169,44 +228,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
         }
+        pending = true;
       }
+      if (FUSE != 0 && pending) { mix_loads(0); mix_loads(1); }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = instr_desc_bf16(kBlockM, P.block_n);
+      const uint32_t idesc_mix = instr_desc_bf16(kBlockM, (FUSE != 0) ? kNHalf : 16);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const TileCoord tc_ = decode_tile(P, tile);
-        const int nk = P.job[tc_.job].ntaps * ksteps_per_tap;
+      int it = 0;        // tiles issued by this CTA
+      int halves = 0;    // mixing halves issued
+      auto mix_mma = [&](int h) {
+        if (h == 0) mbar_wait(bar_a2, (it - 1) & 1);                 // A operand of tile it-1 written (pass 1)
+        mbar_wait(bar_nempty, (halves & 1) ^ 1u);                    // previous half drained by the epilogue
+        tcgen05_fence_after();
+        for (int kc = 0; kc < NF / 64; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + kNormCol, smem_desc_sw128(a2_base + kc * kABytes + kk * 32),
+                      smem_desc_sw128(b_base + stage * b_bytes + kk * 32), idesc_mix, (kc | kk) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_nfull);
+        ++halves;
+      };
+      for (int w = 0; w < nwaves; ++w) {
+        TileCoord tc_;
+        if (!decode_slot(P, w, tc_)) continue;
+        const int nk = P.job[tc_.job].ntaps * P.kchunks;
+        const int ins0 = nk / 2, ins1 = (3 * nk) / 4;
         const int buf = it & 1;
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int k = 0; k < nk; ++k) {
+          if (FUSE != 0 && it > 0) {
+            if (k == ins0) mix_mma(0);
+            if (k == ins1) mix_mma(1);
+          }
           mbar_wait(bar_full + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t a_addr = a_base + stage * kABytes, b_addr = b_base + stage * b_bytes;
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+          for (int kk = 0; kk < kBlockK / 16; ++kk)
             umma_bf16(d_tmem, smem_desc_sw128(a_addr + kk * 32), smem_desc_sw128(b_addr + kk * 32), idesc,
                       (k | kk) != 0 ? 1u : 0u);
-          }
           umma_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs have read it
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(bar_tfull + 8 * buf);       // accumulator complete
+        ++it;
       }
+      if (FUSE != 0 && it > 0) { mix_mma(0); mix_mma(1); }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;               // tile row = pixel
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc_ = decode_tile(P, tile);
+    int halves = 0;
+    for (int w = 0; w < nwaves; ++w) {
+      TileCoord tc_;
+      if (!decode_slot(P, w, tc_)) continue;
       const TcJob& J = P.job[tc_.job];
       const int buf = it & 1;
       const int i = tc_.h0 + row / P.TW, j = tc_.w0 + row % P.TW;
@@ -214,23 +304,128 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(q * 32) << 16);
-      int col = 0;
-      for (; col + 32 <= P.block_n; col += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + col, r);
-        tmem_ld_wait();
-        epilogue_store<32>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
+      const uint32_t taddr = tmem_base + buf * kAccStride + lane_off;
+      if (FUSE == 0) {
+        int col = 0;
+        for (; col + 32 <= P.block_n; col += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + col, r);
+          tmem_ld_wait();
+          epilogue_store<32>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
+        }
+        if (col < P.block_n) {                     // 16-column tail (block_n % 32 == 16)
+          uint32_t r[16];
+          tmem_ld16(taddr + col, r);
+          tmem_ld_wait();
+          epilogue_store<16>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      } else {
+        // ---------- pass 1: accumulator -> (x | g*s) kept in registers as packed bf16, mixing operand -> smem
+        uint32_t keep[NF / 2];
+#pragma unroll
+        for (int c = 0; c < NF / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          uint4 xv[4], sv[4];
+          if (FUSE == 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              xv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
+              sv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
+                            : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+            }
+          }
+          tmem_ld_wait();
+          uint32_t a2w[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            if (FUSE == 1) {
+              v0 += s_bias[c * 32 + 2 * e];
+              v1 += s_bias[c * 32 + 2 * e + 1];
+              const uint32_t xb = pack_bf16(v0, v1);
+              keep[c * 16 + e] = xb;
+              const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);       // the stored (bf16) x is what the mixing sees
+              a2w[e] = pack_bf16(x0 * x0, x1 * x1);
+            } else {
+              const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[e >> 2])[e & 3];
+              const uint32_t sw = reinterpret_cast<const uint32_t*>(&sv[e >> 2])[e & 3];
+              const float x0 = bf16_lo(xw), x1 = bf16_hi(xw), s0 = bf16_lo(sw), s1 = bf16_hi(sw);
+              keep[c * 16 + e] = pack_bf16(v0 * s0, v1 * s1);
+              a2w[e] = pack_bf16(v0 * x0 / s0, v1 * x1 / s1);
+            }
+          }
+          if (FUSE == 1 && valid) {
+            uint4* xp = reinterpret_cast<uint4*>(P.xpre_out + off0 + c * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              xp[u] = make_uint4(keep[c * 16 + 4 * u], keep[c * 16 + 4 * u + 1], keep[c * 16 + 4 * u + 2],
+                                 keep[c * 16 + 4 * u + 3]);
+          }
+          // 32 columns = 4 x 16-byte chunks of K-chunk (c/2), chunk index ((c&1)*4 + u) within the 128-byte row
+          uint8_t* a2c = a2_ptr + (c >> 1) * kABytes;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(a2c + sw128_offset(row, (c & 1) * 4 + u)) =
+                make_uint4(a2w[4 * u], a2w[4 * u + 1], a2w[4 * u + 2], a2w[4 * u + 3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_a2);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        // ---------- pass 2: two halves of the mixing result
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_nfull, halves & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < kNHalf / 32; ++cc) {
+            const int c = h * (kNHalf / 32) + cc;                    // 32-column chunk index within the tile
+            uint32_t r[32];
+            tmem_ld32(tmem_base + kNormCol + lane_off + cc * 32, r);
+            uint4 xv[4];
+            if (FUSE == 2) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                xv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
+            }
+            tmem_ld_wait();
+            uint32_t o[16], so[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
+              const uint32_t kw = keep[c * 16 + e];
+              if (FUSE == 1) {
+                const float s0 = sqrtf(m0 + s_bias[256 + c * 32 + 2 * e]), s1 = sqrtf(m1 + s_bias[256 + c * 32 + 2 * e + 1]);
+                o[e] = pack_bf16(bf16_lo(kw) * s0, bf16_hi(kw) * s1);
+                so[e] = pack_bf16(s0, s1);
+              } else {
+                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[e >> 2])[e & 3];
+                o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
+              }
+            }
+            if (valid) {
+              uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + off0 + c * 32);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+              if (FUSE == 1) {
+                uint4* sp = reinterpret_cast<uint4*>(P.s_out + off0 + c * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sp[u] = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_nempty);
+          ++halves;
+        }
       }
-      if (col < P.block_n) {                     // 16-column tail (block_n % 32 == 16)
-        uint32_t r[16];
-        tmem_ld16(taddr + col, r);
-        tmem_ld_wait();
-        epilogue_store<16>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      ++it;
     }
   }
 
@@ -287,6 +482,7 @@ struct TcConv {
   TcParams P;
   int smem_bytes;
   int grid;
+  int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
 };
 
 static int pick_block_n(int Nn) {
@@ -295,12 +491,26 @@ static int pick_block_n(int Nn) {
   return 0;
 }
 
-int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, TcConv** out) {
+typedef void (*TcKernel)(const TcParams);
+static TcKernel select_kernel(int fuse, int nf) {
+  if (fuse == 0) return k_conv_tc<0, 64>;
+  if (fuse == 1) return nf == 192 ? k_conv_tc<1, 192> : (nf == 128 ? k_conv_tc<1, 128> : k_conv_tc<1, 64>);
+  return nf == 192 ? k_conv_tc<2, 192> : (nf == 128 ? k_conv_tc<2, 128> : k_conv_tc<2, 64>);
+}
+
+bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192; }
+
+int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, int fuse,
+                   const __nv_bfloat16* mix_op, TcConv** out) {
   const ConvGeom& g = plan.g;
   SGA_CHECK(g.Cin % 8 == 0, "tcgen05 conv needs Cin %% 8 == 0 (got %d)", g.Cin);
   SGA_CHECK(g.Cout % 16 == 0 && g.Cout <= 512, "tcgen05 conv needs Cout %% 16 == 0 and <= 512 (got %d)", g.Cout);
+  SGA_CHECK(fuse == 0 || (tc_conv_can_fuse(g.Cout) && mix_op != nullptr), "IGDN fusion needs Cout in {64,128,192}");
+  for (int jn = 1; jn < plan.njobs; ++jn)
+    SGA_CHECK(plan.job[jn].Ho == plan.job[0].Ho && plan.job[jn].Wo == plan.job[0].Wo, "jobs of a plan must share a grid");
   TcConv* c = new TcConv();
   memset(&c->P, 0, sizeof(c->P));
+  c->fuse = fuse;
   TcParams& P = c->P;
   P.N = g.N; P.K = g.Cin; P.Nn = g.Cout;
   P.block_n = pick_block_n(g.Cout);
@@ -312,26 +522,28 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   const int Wo0 = plan.job[0].Wo;
   P.TW = (Wo0 >= 16) ? 16 : 8;
   P.TH = kBlockM / P.TW;
+  P.tiles_h = ceil_div(plan.job[0].Ho, P.TH);
+  P.tiles_w = ceil_div(plan.job[0].Wo, P.TW);
+  P.n_spatial = g.N * P.tiles_h * P.tiles_w * P.n_tiles_n;
   const int b_bytes = P.block_n * kBlockK * 2;
-  int stages = (227 * 1024 - 1024 - 512 * 4 - 256) / (kABytes + b_bytes);
+  const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
+  const int fixed = 1024 + a2_bytes + 512 * 4 + 256;
+  int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  SGA_CHECK(stages >= 2, "not enough shared memory for the pipeline");
   P.stages = stages;
-  c->smem_bytes = 1024 + stages * (kABytes + b_bytes) + 512 * 4 + 256;
-  int ntap = 0, ntile = 0;
+  c->smem_bytes = fixed + stages * (kABytes + b_bytes);
+  int ntap = 0;
   for (int jn = 0; jn < plan.njobs; ++jn) {
     const ConvJobPlan& jp = plan.job[jn];
     TcJob& J = P.job[jn];
     J.tap_begin = ntap; J.ntaps = jp.ntaps;
     for (int t = 0; t < jp.ntaps; ++t) P.taps[ntap++] = jp.taps[t];
     J.Ho = jp.Ho; J.Wo = jp.Wo;
-    J.tiles_h = ceil_div(jp.Ho, P.TH); J.tiles_w = ceil_div(jp.Wo, P.TW);
-    J.tile_begin = ntile;
-    ntile += g.N * J.tiles_h * J.tiles_w * P.n_tiles_n;
     J.out_off = (jp.out_phase_stride == 2) ? (static_cast<long long>(jp.out_py) * g.Wout + jp.out_px) * g.Cout : 0;
     J.oH = static_cast<long long>(jp.out_phase_stride) * g.Wout * g.Cout;
     J.oW = static_cast<long long>(jp.out_phase_stride) * g.Cout;
   }
-  P.total_tiles = ntile;
   // input views (identical for every job of a plan)
   const ConvJobPlan& j0 = plan.job[0];
   for (int v = 0; v < kMaxViews; ++v) {
@@ -357,15 +569,19 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
   }
+  if (fuse) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(g.Cout)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(g.Cout) * 2};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(g.Cout / 2)};
+    int st = tma_encode_tiled(&P.gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, mix_op, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st != SGA_OK) { delete c; return st; }
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c->grid = (ntile < sms) ? ntile : sms;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SGA_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  c->grid = (P.n_spatial < sms) ? P.n_spatial : sms;
+  SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return SGA_OK;
 }
@@ -374,10 +590,33 @@ void tc_conv_destroy(TcConv* c) { delete c; }
 
 int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bfloat16* relu_mask, __nv_bfloat16* out_bf16,
                    float* out_f32, cudaStream_t st) {
-  if (c->P.total_tiles == 0) return SGA_OK;
+  SGA_CHECK(c->fuse == 0, "fused conv must be launched with tc_conv_launch_igdn_*");
+  if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.bias = bias; P.relu = relu; P.mask = relu_mask; P.out_bf16 = out_bf16; P.out_f32 = out_f32;
-  k_conv_tc<<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  k_conv_tc<0, 64><<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int tc_conv_launch_igdn_fwd(const TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
+                            __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st) {
+  SGA_CHECK(c->fuse == 1, "conv was not created with forward IGDN fusion");
+  if (c->P.n_spatial == 0) return SGA_OK;
+  TcParams P = c->P;
+  P.bias = bias; P.beta = beta; P.xpre_out = xpre_out; P.s_out = s_out; P.out_bf16 = act_out;
+  select_kernel(1, P.Nn)<<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
+                            __nv_bfloat16* gx_out, cudaStream_t st) {
+  SGA_CHECK(c->fuse == 2, "conv was not created with backward IGDN fusion");
+  if (c->P.n_spatial == 0) return SGA_OK;
+  TcParams P = c->P;
+  P.x_in = x_saved; P.s_in = s_saved; P.out_bf16 = gx_out;
+  select_kernel(2, P.Nn)<<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

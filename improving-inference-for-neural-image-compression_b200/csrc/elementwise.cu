@@ -38,7 +38,8 @@ __device__ __forceinline__ float soft_round_one(float v, float u0, float u1, flo
 }
 
 __device__ __forceinline__ void pair_uniforms(const float* __restrict__ inj, long long numel, long long e0,
-                                              uint64_t seed, int step, int tensor_id, float u[4]) {
+                                              uint64_t seed, int step, int tensor_id, float u[4],
+                                              long long ctr_off = 0) {
   if (inj != nullptr) {  // injected: [2][numel], DOWN logits first
     u[0] = inj[e0];
     u[1] = inj[numel + e0];
@@ -46,7 +47,7 @@ __device__ __forceinline__ void pair_uniforms(const float* __restrict__ inj, lon
     u[2] = has2 ? inj[e0 + 1] : 0.5f;
     u[3] = has2 ? inj[numel + e0 + 1] : 0.5f;
   } else {
-    const Philox4 r = philox4x32_10(static_cast<uint32_t>(e0 >> 1), static_cast<uint32_t>(step),
+    const Philox4 r = philox4x32_10(static_cast<uint32_t>((e0 + ctr_off) >> 1), static_cast<uint32_t>(step),
                                     static_cast<uint32_t>(tensor_id), 0u, static_cast<uint32_t>(seed),
                                     static_cast<uint32_t>(seed >> 32));
     u[0] = bits_to_uniform(r.x);
@@ -185,7 +186,7 @@ template <typename AT>
 __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ inj, long long numel,
                          long long per_image, int C, const float* __restrict__ pk, float T, float eps, uint64_t seed,
                          int step, int hard, float rate_scale, AT* __restrict__ zt_act, float* __restrict__ g_rate,
-                         float* __restrict__ dz, double* __restrict__ bits) {
+                         float* __restrict__ dz, double* __restrict__ bits, long long ctr_off) {
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long e0 = pair * 2;
   float nll = 0.0f;
@@ -193,7 +194,7 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
   if (e0 < numel) {
     img = e0 / per_image;
     float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-    if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Z, u);
+    if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Z, u, ctr_off);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const long long e = e0 + k;
@@ -263,7 +264,7 @@ template <typename AT>
 __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ inj, const float* __restrict__ h2,
                          int N, int Hy, int Wy, int Hh, int Wh, int C, float T, float eps, uint64_t seed, int step,
                          int hard, float rate_scale, AT* __restrict__ yt_act, float* __restrict__ g_rate,
-                         float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits) {
+                         float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits, long long ctr_off) {
   const int halfC = C >> 1;
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long npairs = static_cast<long long>(N) * Hh * Wh * halfC;
@@ -283,7 +284,7 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
       const long long numel = static_cast<long long>(N) * Hy * Wy * C;
       const long long e0 = ((static_cast<long long>(n) * Hy + i) * Wy + j) * C + c;
       float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-      if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u);
+      if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u, ctr_off);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const long long e = e0 + k;
@@ -498,34 +499,34 @@ int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, l
 template <typename AT>
 int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
-                  float* dz, double* bits, cudaStream_t st) {
+                  float* dz, double* bits, long long ctr_off, cudaStream_t st) {
   const long long pairs = (numel + 1) / 2;
   k_z_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(z, inj, numel, per_image, C, pk, T, eps, seed, step, hard,
-                                                       rate_scale, zt_act, g_rate, dz, bits);
+                                                       rate_scale, zt_act, g_rate, dz, bits, ctr_off);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
 template int launch_z_path<float>(const float*, const float*, long long, long long, int, const float*, float, float,
-                                  uint64_t, int, int, float, float*, float*, float*, double*, cudaStream_t);
+                                  uint64_t, int, int, float, float*, float*, float*, double*, long long, cudaStream_t);
 template int launch_z_path<__nv_bfloat16>(const float*, const float*, long long, long long, int, const float*, float,
                                           float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*, double*,
-                                          cudaStream_t);
+                                          long long, cudaStream_t);
 
 template <typename AT>
 int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
-                  float* dy, AT* g_h2, double* bits, cudaStream_t st) {
+                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st) {
   const long long pairs = static_cast<long long>(N) * Hh * Wh * (C / 2);
   k_y_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step, hard,
-                                                       rate_scale, yt_act, g_rate, dy, g_h2, bits);
+                                                       rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
 template int launch_y_path<float>(const float*, const float*, const float*, int, int, int, int, int, int, float, float,
-                                  uint64_t, int, int, float, float*, float*, float*, float*, double*, cudaStream_t);
+                                  uint64_t, int, int, float, float*, float*, float*, float*, double*, long long, cudaStream_t);
 template int launch_y_path<__nv_bfloat16>(const float*, const float*, const float*, int, int, int, int, int, int, float,
                                           float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*,
-                                          __nv_bfloat16*, double*, cudaStream_t);
+                                          __nv_bfloat16*, double*, long long, cudaStream_t);
 
 int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
                       double* sse, double* sse_r, cudaStream_t st) {

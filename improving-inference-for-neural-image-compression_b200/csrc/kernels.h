@@ -18,11 +18,11 @@ int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, l
 template <typename AT>
 int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
-                  float* dz, double* bits, cudaStream_t st);
+                  float* dz, double* bits, long long ctr_off, cudaStream_t st);
 template <typename AT>
 int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
-                  float* dy, AT* g_h2, double* bits, cudaStream_t st);
+                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st);
 int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
                       double* sse, double* sse_r, cudaStream_t st);
 int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st);
@@ -70,11 +70,21 @@ int launch_transpose_taps(const float* w_ref, int taps, int Cin, int Cout, float
 
 // ---- conv_tc.cu : bf16 tcgen05 implicit GEMM
 struct TcConv;  // opaque: tensor maps + tap tables for one layer at one shape
-int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, TcConv** out);
+// fuse: 0 = plain epilogue, 1 = + IGDN forward, 2 = + IGDN backward (mix_op = K-major bf16 [C][C] mixing operand:
+// gamma^T for forward, gamma for backward); fusion needs Cout in {64,128,192}
+bool tc_conv_can_fuse(int cout);
+int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, int fuse,
+                   const __nv_bfloat16* mix_op, TcConv** out);
 void tc_conv_destroy(TcConv* c);
 // epilogue: v = acc + bias[n]; relu; *= (mask > 0); store as bf16 (out_bf16) and/or fp32 (out_f32)
 int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bfloat16* relu_mask, __nv_bfloat16* out_bf16,
                    float* out_f32, cudaStream_t st);
+// x = acc + bias; s = sqrt(beta + x^2 @ gamma); act = x*s  -- all three stored as bf16
+int tc_conv_launch_igdn_fwd(const TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
+                            __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st);
+// g = acc; g_x = g*s + x*((g*x/s) @ gamma^T) stored as bf16
+int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
+                            __nv_bfloat16* gx_out, cudaStream_t st);
 // w_ref (kh,kw,Cin,Cout) fp32 -> K-major bf16 B operand: [tap][Nn][K] (K = Cin for forward kinds, Cout for dgrads)
 int launch_pack_weights_bf16(const float* w_ref, int taps, int Cin, int Cout, bool transposed, __nv_bfloat16* out,
                              cudaStream_t st);

@@ -28,7 +28,7 @@ class SgaEngine:
     """One context = one GPU = one shard of images of a reference batch."""
 
     def __init__(self, weights, n_images, height, width, num_filters, lmbda, n_ref=None, operand="bf16", seed=0,
-                 lr=0.005, beta1=0.9, beta2=0.999, adam_eps=1e-8, clip_eps=1e-5, device=None):
+                 lr=0.005, beta1=0.9, beta2=0.999, adam_eps=1e-8, clip_eps=1e-5, device=None, first_image=0):
         if not torch.cuda.is_available():
             raise _lib.SgaError("sga_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -38,7 +38,7 @@ class SgaEngine:
             n_images=n_images, height=height, width=width, num_filters=num_filters,
             n_ref=n_images if n_ref is None else n_ref,
             operand={"f32": _lib.OPERAND_F32, "bf16": _lib.OPERAND_BF16}[operand],
-            lmbda=lmbda, lr=lr, beta1=beta1, beta2=beta2, adam_eps=adam_eps, clip_eps=clip_eps, seed=seed)
+            lmbda=lmbda, lr=lr, beta1=beta1, beta2=beta2, adam_eps=adam_eps, clip_eps=clip_eps, seed=seed, first_image=first_image)
         self.n, self.h, self.w, self.c = n_images, height, width, num_filters
         self.ctx = ctypes.c_void_p()
         _lib.check(self.lib.sga_create(ctypes.byref(self.cfg), ctypes.byref(self.ctx)))

@@ -51,6 +51,9 @@ typedef struct {
   float lr, beta1, beta2, adam_eps;   /* adam.py:9-10 ; sga.py:190 uses lr = 0.005 */
   float clip_eps;          /* epsilon of the atanh clip, 1e-5 (sga.py:30) */
   uint64_t seed;           /* key of the Philox4x32-10 Gumbel noise stream */
+  int32_t first_image;     /* index of this shard's first image inside the reference batch: the noise counter is the
+                              element index inside the WHOLE batch, so results do not depend on the sharding */
+  int32_t reserved_;
 } sga_config;
 
 /* Weights in the reference's variable layout (float32 device pointers; kernels (kh,kw,Cin,Cout),

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.sga_version() >= 100
-    assert ctypes.sizeof(_lib.SgaConfig) == 56
+    assert ctypes.sizeof(_lib.SgaConfig) == 64
 
 
 def test_no_cpu_fallback_without_cuda():
