@@ -2,6 +2,7 @@
 // orchestration of the SGA graph (reference sga.py:88-174, 207-215, 240-247) on one CUDA stream.
 #include <stdarg.h>
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "kernels.h"
@@ -284,15 +285,15 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   if (stats) PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
   // ---- backward
   if (g.lmbda > 0.0f) {
-    PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
     if (c->fused) {
-      // IGDN_2 backward stands alone (its producer is the layer-3 dgrad); IGDN_1 / IGDN_0 backward run in the epilogues
-      // of the dgrad convs that produce their upstream gradients
-      PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_xpre[2], c->b_s[2], c->b_gb[2], st));
+      // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
+      // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
+      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_xpre[2], c->b_s[2], c->b_gb[2], st));
       PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_xpre[1], c->b_s[1], c->b_gb[1], st));
       PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_xpre[0], c->b_s[0], c->b_gb[0], st));
       PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
     } else {
+      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
       for (int i = 2; i >= 0; --i) {
         PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
         if (i == 0) PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
@@ -446,7 +447,7 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
     SGA_TRY(make_tc(kS1TrueDgrad, c->hs[2], d.N, d.Hh, d.Wh, c->b_gh2, &c->tc_hs_d[2]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[1], d.N, d.Hh, d.Wh, c->b_gh1, &c->tc_hs_d[1]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[0], d.N, 2 * d.Hz, 2 * d.Wz, c->b_gh0, &c->tc_hs_d[0]));
-    c->fused = tc_conv_can_fuse(C);
+    c->fused = tc_conv_can_fuse(C) && getenv("SGA_NO_FUSE") == nullptr;
     for (int i = 0; i < 3; ++i) {
       const bf16* in = (i == 0) ? c->b_yt : c->b_act[i - 1];
       const long long pix = static_cast<long long>(d.N) * d.Hs[i + 1] * d.Ws[i + 1];
@@ -456,7 +457,6 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
         if (i > 0) SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i], 2,
                                    c->gs_gamma_b[i - 1]));
         else SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i]));
-        if (i == 2) SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
       } else {
         SGA_TRY(make_tc(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, &c->tc_gs[i]));
         SGA_TRY(make_tc(kUp2Dgrad, c->gs[i], d.N, d.Hs[i + 1], d.Ws[i + 1], c->b_gb[i], &c->tc_gs_d[i]));
@@ -466,7 +466,8 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
     }
     SGA_TRY(c->alloc(&c->l3_wscatter, 80 * C)); SGA_TRY(c->alloc(&c->l3_wgather, 80 * C));
     SGA_TRY(l3_pack_weights(c->gs[3].w, C, c->l3_wscatter, c->l3_wgather, st));
-    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, d.N, d.Hs[3], d.Ws[3], C, d.H, d.W, &c->l3));
+    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, c->fused ? c->gs_gamma_b[2] : nullptr, d.N, d.Hs[3],
+                         d.Ws[3], C, d.H, d.W, &c->l3));
     SGA_CUDA(cudaStreamSynchronize(st));
   }
   c->bound = true;

@@ -8,7 +8,9 @@
 //            the box lands in shared memory as a K-major SWIZZLE_128B operand tile (128 rows x 128 B)
 //   B tile : TMA 2-D box {64 ch, BLOCK_N} of the pre-packed K-major weights [tap][Cout][Cin]
 //   MMA    : 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) accumulating in TMEM (fp32)
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then G groups of 4 epilogue warps (one warp
+// per TMEM lane quarter; the groups split the accumulator columns) -- the epilogue must finish a tile faster than the
+// tensor pipe does (~6 us for a 128x192 tile of the widest layer), which 4 warps cannot do for the fused variants.
 // Persistent CTAs (one per SM); the TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Tiles are issued in waves of gridDim.x spatial tiles per output phase, so the 4 phases of a transposed
 // conv re-read their (shared) input from L2 instead of HBM and every CTA gets the same mix of 9/6/6/4-tap tiles.
@@ -24,12 +26,13 @@
 #include "kernels.h"
 #include "tc_kernels.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace sga {
 
 using namespace tc;
 
-constexpr int kTcThreads = 192;
+constexpr int kPlainGroups = 2;                  // epilogue warp groups of the un-fused kernel
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
@@ -54,6 +57,8 @@ struct alignas(64) TcParams {
   int TH, TW, tiles_h, tiles_w;
   int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
   int relu;
+  int dbg;                // debug/timing experiments only (env SGA_DBG): 1 skip xpre store, 2 skip s store, 4 skip out store
+  int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
   long long oN;
   const float* bias;
   const __nv_bfloat16* mask;
@@ -126,9 +131,24 @@ __device__ __forceinline__ void epilogue_store(const TcParams& P, const uint32_t
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // FUSE: 0 = plain conv epilogue, 1 = + IGDN forward, 2 = + IGDN backward.  NF = Cout of the fused variants.
-template <int FUSE, int NF>
-__global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcParams P) {
+// G = number of epilogue warp groups (4 warps each: one per TMEM lane quarter); the groups split the accumulator
+// columns in 32-column chunks.  Fused variants use G = NF/64, so every epilogue warp owns exactly one chunk in each
+// half of the tile (chunk grp of half 0, chunk grp of half 1) and keeps its point-wise state in registers.
+template <int FUSE, int NF, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_constant__ TcParams P) {
+  static_assert(FUSE == 0 || G * 64 == NF, "fused variants: one 32-column chunk per warp and half");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -174,11 +194,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);
+      mbar_init(bar_tempty + 8 * b, 4 * G);
     }
-    mbar_init(bar_a2, 128);
+    mbar_init(bar_a2, 128 * G);
     mbar_init(bar_nfull, 1);
-    mbar_init(bar_nempty, 4);
+    mbar_init(bar_nempty, 4 * G);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -210,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
         if (!decode_slot(P, w, tc_)) continue;
         const TcJob& J = P.job[tc_.job];
         const int nk = J.ntaps * P.kchunks;
-        const int ins0 = nk / 2, ins1 = (3 * nk) / 4;
+        const int ins0 = (P.mix_at0 * nk) / 8, ins1 = (P.mix_at1 * nk) / 8 < nk ? (P.mix_at1 * nk) / 8 : nk - 1;
         int k = 0;
         for (int t = 0; t < J.ntaps; ++t) {
           const Tap tap = P.taps[J.tap_begin + t];
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
         TileCoord tc_;
         if (!decode_slot(P, w, tc_)) continue;
         const int nk = P.job[tc_.job].ntaps * P.kchunks;
-        const int ins0 = nk / 2, ins1 = (3 * nk) / 4;
+        const int ins0 = (P.mix_at0 * nk) / 8, ins1 = (P.mix_at1 * nk) / 8 < nk ? (P.mix_at1 * nk) / 8 : nk - 1;
         const int buf = it & 1;
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
         tcgen05_fence_after();
@@ -288,8 +308,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
       if (FUSE != 0 && it > 0) { mix_mma(0); mix_mma(1); }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 .. 2+4G) =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;             // column group
     const int row = q * 32 + lane;               // tile row = pixel
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     int it = 0;
@@ -302,68 +323,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
       const int i = tc_.h0 + row / P.TW, j = tc_.w0 + row % P.TW;
       const bool valid = (i < J.Ho) && (j < J.Wo);
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
+      // fused backward: the saved x / s of this warp's two chunks are fetched before the accumulator is awaited
+      uint4 xin[(FUSE == 2) ? 2 : 1][4], sin[(FUSE == 2) ? 2 : 1][4];
+      if (FUSE == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = grp + h * G;
+            xin[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
+            sin[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
+                              : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+          }
+      }
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + lane_off;
       if (FUSE == 0) {
-        int col = 0;
-        for (; col + 32 <= P.block_n; col += 32) {
+        const int nfull = P.block_n >> 5;
+        for (int c = grp; c < nfull; c += G) {
           uint32_t r[32];
-          tmem_ld32(taddr + col, r);
+          tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
-          epilogue_store<32>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
+          epilogue_store<32>(P, r, s_bias, tc_.n0 + c * 32, off0 + c * 32, valid);
         }
-        if (col < P.block_n) {                     // 16-column tail (block_n % 32 == 16)
+        if ((P.block_n & 31) != 0 && (nfull % G) == grp) {   // 16-column tail (block_n % 32 == 16)
           uint32_t r[16];
-          tmem_ld16(taddr + col, r);
+          tmem_ld16(taddr + nfull * 32, r);
           tmem_ld_wait();
-          epilogue_store<16>(P, r, s_bias, tc_.n0 + col, off0 + col, valid);
+          epilogue_store<16>(P, r, s_bias, tc_.n0 + nfull * 32, off0 + nfull * 32, valid);
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       } else {
         // ---------- pass 1: accumulator -> (x | g*s) kept in registers as packed bf16, mixing operand -> smem
-        uint32_t keep[NF / 2];
+        uint32_t keep[2][16];
 #pragma unroll
-        for (int c = 0; c < NF / 32; ++c) {
+        for (int h = 0; h < 2; ++h) {
+          const int c = grp + h * G;               // 32-column chunk of the tile owned by this warp in half h
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
-          uint4 xv[4], sv[4];
-          if (FUSE == 2) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              xv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
-              sv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
-                            : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-            }
-          }
           tmem_ld_wait();
           uint32_t a2w[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-            if (FUSE == 1) {
-              v0 += s_bias[c * 32 + 2 * e];
-              v1 += s_bias[c * 32 + 2 * e + 1];
-              const uint32_t xb = pack_bf16(v0, v1);
-              keep[c * 16 + e] = xb;
-              const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);       // the stored (bf16) x is what the mixing sees
-              a2w[e] = pack_bf16(x0 * x0, x1 * x1);
-            } else {
-              const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[e >> 2])[e & 3];
-              const uint32_t sw = reinterpret_cast<const uint32_t*>(&sv[e >> 2])[e & 3];
-              const float x0 = bf16_lo(xw), x1 = bf16_hi(xw), s0 = bf16_lo(sw), s1 = bf16_hi(sw);
-              keep[c * 16 + e] = pack_bf16(v0 * s0, v1 * s1);
-              a2w[e] = pack_bf16(v0 * x0 / s0, v1 * x1 / s1);
+          for (int e4 = 0; e4 < 8; ++e4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FUSE == 1) b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * e4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = e4 * 2 + e2;
+              float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+              if (FUSE == 1) {
+                v0 += bb[2 * e2];
+                v1 += bb[2 * e2 + 1];
+                const uint32_t xb = pack_bf16(v0, v1);
+                keep[h][e] = xb;
+                const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);     // the stored (bf16) x is what the mixing sees
+                a2w[e] = pack_bf16(x0 * x0, x1 * x1);
+              } else {
+                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
+                const uint32_t sw = reinterpret_cast<const uint32_t*>(&sin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
+                const float x0 = bf16_lo(xw), x1 = bf16_hi(xw), s0 = bf16_lo(sw), s1 = bf16_hi(sw);
+                keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
+                a2w[e] = pack_bf16(v0 * x0 * fast_rcp(s0), v1 * x1 * fast_rcp(s1));
+              }
             }
           }
-          if (FUSE == 1 && valid) {
+          if (FUSE == 1 && valid && !(P.dbg & 1)) {
             uint4* xp = reinterpret_cast<uint4*>(P.xpre_out + off0 + c * 32);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              xp[u] = make_uint4(keep[c * 16 + 4 * u], keep[c * 16 + 4 * u + 1], keep[c * 16 + 4 * u + 2],
-                                 keep[c * 16 + 4 * u + 3]);
+              xp[u] = make_uint4(keep[h][4 * u], keep[h][4 * u + 1], keep[h][4 * u + 2], keep[h][4 * u + 3]);
           }
           // 32 columns = 4 x 16-byte chunks of K-chunk (c/2), chunk index ((c&1)*4 + u) within the 128-byte row
           uint8_t* a2c = a2_ptr + (c >> 1) * kABytes;
@@ -377,52 +409,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        // ---------- pass 2: two halves of the mixing result
+        // ---------- pass 2: two halves of the mixing result; this warp owns chunk `grp` of each half
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          const int c = grp + h * G;
           mbar_wait(bar_nfull, halves & 1);
           tcgen05_fence_after();
+          uint32_t r[32];
+          tmem_ld32(tmem_base + kNormCol + lane_off + grp * 32, r);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_nempty);       // the mixing result is in registers: release the TMEM region
+          ++halves;
+          uint32_t o[16], so[16];
 #pragma unroll
-          for (int cc = 0; cc < kNHalf / 32; ++cc) {
-            const int c = h * (kNHalf / 32) + cc;                    // 32-column chunk index within the tile
-            uint32_t r[32];
-            tmem_ld32(tmem_base + kNormCol + lane_off + cc * 32, r);
-            uint4 xv[4];
-            if (FUSE == 2) {
+          for (int e4 = 0; e4 < 8; ++e4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FUSE == 1) b4 = *reinterpret_cast<const float4*>(s_bias + 256 + c * 32 + 4 * e4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                xv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
-            }
-            tmem_ld_wait();
-            uint32_t o[16], so[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = e4 * 2 + e2;
               const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
-              const uint32_t kw = keep[c * 16 + e];
+              const uint32_t kw = keep[h][e];
               if (FUSE == 1) {
-                const float s0 = sqrtf(m0 + s_bias[256 + c * 32 + 2 * e]), s1 = sqrtf(m1 + s_bias[256 + c * 32 + 2 * e + 1]);
+                const float s0 = fast_sqrt(m0 + bb[2 * e2]), s1 = fast_sqrt(m1 + bb[2 * e2 + 1]);
                 o[e] = pack_bf16(bf16_lo(kw) * s0, bf16_hi(kw) * s1);
                 so[e] = pack_bf16(s0, s1);
               } else {
-                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[e >> 2])[e & 3];
+                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
                 o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
               }
             }
-            if (valid) {
-              uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + off0 + c * 32);
+          }
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + off0 + c * 32);
+            if (!(P.dbg & 4)) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-              if (FUSE == 1) {
-                uint4* sp = reinterpret_cast<uint4*>(P.s_out + off0 + c * 32);
+            }
+            if (FUSE == 1 && !(P.dbg & 2)) {
+              uint4* sp = reinterpret_cast<uint4*>(P.s_out + off0 + c * 32);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) sp[u] = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
-              }
+              for (int u = 0; u < 4; ++u) sp[u] = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
             }
           }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_nempty);
-          ++halves;
         }
       }
       ++it;
@@ -493,10 +525,11 @@ static int pick_block_n(int Nn) {
 
 typedef void (*TcKernel)(const TcParams);
 static TcKernel select_kernel(int fuse, int nf) {
-  if (fuse == 0) return k_conv_tc<0, 64>;
-  if (fuse == 1) return nf == 192 ? k_conv_tc<1, 192> : (nf == 128 ? k_conv_tc<1, 128> : k_conv_tc<1, 64>);
-  return nf == 192 ? k_conv_tc<2, 192> : (nf == 128 ? k_conv_tc<2, 128> : k_conv_tc<2, 64>);
+  if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups>;
+  if (fuse == 1) return nf == 192 ? k_conv_tc<1, 192, 3> : (nf == 128 ? k_conv_tc<1, 128, 2> : k_conv_tc<1, 64, 1>);
+  return nf == 192 ? k_conv_tc<2, 192, 3> : (nf == 128 ? k_conv_tc<2, 128, 2> : k_conv_tc<2, 64, 1>);
 }
+static int kernel_threads(int fuse, int nf) { return 64 + 128 * (fuse == 0 ? kPlainGroups : nf / 64); }
 
 bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192; }
 
@@ -517,6 +550,12 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.n_tiles_n = g.Cout / P.block_n;
   P.kchunks = ceil_div(g.Cin, kBlockK);
   P.njobs = plan.njobs;
+  {
+    const char* e0 = getenv("SGA_MIX_AT0"); const char* e1 = getenv("SGA_MIX_AT1");
+    P.mix_at0 = e0 ? atoi(e0) : 6; P.mix_at1 = e1 ? atoi(e1) : 8;
+    const char* ed = getenv("SGA_DBG");
+    P.dbg = ed ? atoi(ed) : 0;
+  }
   P.oN = static_cast<long long>(g.Hout) * g.Wout * g.Cout;
   // spatial tile: 128 pixels = TH x TW
   const int Wo0 = plan.job[0].Wo;
@@ -530,6 +569,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   const int fixed = 1024 + a2_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* es = getenv("SGA_DBG_STAGES")) { const int v = atoi(es); if (v >= 2 && v < stages) stages = v; }
   SGA_CHECK(stages >= 2, "not enough shared memory for the pipeline");
   P.stages = stages;
   c->smem_bytes = fixed + stages * (kABytes + b_bytes);
@@ -594,7 +634,7 @@ int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bflo
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.bias = bias; P.relu = relu; P.mask = relu_mask; P.out_bf16 = out_bf16; P.out_f32 = out_f32;
-  k_conv_tc<0, 64><<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  k_conv_tc<0, 64, kPlainGroups><<<c->grid, kernel_threads(0, 0), c->smem_bytes, st>>>(P);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -605,7 +645,7 @@ int tc_conv_launch_igdn_fwd(const TcConv* c, const float* bias, const float* bet
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.bias = bias; P.beta = beta; P.xpre_out = xpre_out; P.s_out = s_out; P.out_bf16 = act_out;
-  select_kernel(1, P.Nn)<<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  select_kernel(1, P.Nn)<<<c->grid, kernel_threads(1, P.Nn), c->smem_bytes, st>>>(P);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -616,7 +656,7 @@ int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.x_in = x_saved; P.s_in = s_saved; P.out_bf16 = gx_out;
-  select_kernel(2, P.Nn)<<<c->grid, kTcThreads, c->smem_bytes, st>>>(P);
+  select_kernel(2, P.Nn)<<<c->grid, kernel_threads(2, P.Nn), c->smem_bytes, st>>>(P);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

@@ -20,7 +20,7 @@ using namespace tc;
 // =====================================================================================================
 // forward
 // =====================================================================================================
-constexpr int kL3Threads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kL3Threads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue of even / odd tiles
 constexpr int kL3Stages = 5;
 constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
@@ -114,10 +114,15 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       }
     }
   } else {
+    // Two epilogue groups of 4 warps: group g drains the tiles with (it & 1) == g, i.e. TMEM / P buffer g.  The x
+    // values of a thread's output pixels are fetched one tile ahead (the col2im loop is otherwise bound by that latency).
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;        // 0..127 among epilogue threads
+    const int et = (threadIdx.x - 64) & 127;   // 0..127 inside the group
     const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
+    constexpr int kPix = 2 * kL3IntH * 2 * kL3IntW;         // 336 output pixels per tile
+    constexpr int kPer = (kPix + 127) / 128;                // 3 per thread
     float acc_s = 0.0f, acc_r = 0.0f;
     int acc_img = -1;
     auto flush = [&]() {
@@ -128,12 +133,34 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       }
       acc_s = 0.0f; acc_r = 0.0f;
     };
-    int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    float xn[kPer][3];
+    auto fetch_x = [&](int tile) {
       const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
       const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
-      const int buf = it & 1;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int p = et + k * 128;
+        const int oy = 2 * hi0 + p / (2 * kL3IntW), ox = 2 * wi0 + p % (2 * kL3IntW);
+        const bool in = (p < kPix) && (oy < P.H) && (ox < P.W);
+        const float* xp = P.x + ((static_cast<long long>(img) * P.H + oy) * P.W + ox) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xn[k][c] = in ? __ldg(xp + c) : 0.0f;
+      }
+    };
+    const int first = blockIdx.x + grp * gridDim.x;
+    if (first < P.total_tiles) fetch_x(first);
+    int it = grp;
+    for (int tile = first; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
+      const int buf = grp;
       if (img != acc_img) { flush(); acc_img = img; }   // warp-uniform
+      float xc[kPer][3];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xc[k][c] = xn[k][c];
+      if (tile + 2 * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tile + 2 * gridDim.x);
       float* Pb = Ps + buf * 128 * kPsStride;
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
@@ -155,10 +182,13 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
         for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 64 + k] = __uint_as_float(r2[k]);
       }
       tcgen05_fence_before();
-      named_bar_sync(1, 128);                 // all 128 rows of P are in shared memory; TMEM buffer drained
+      named_bar_sync(1 + grp, 128);           // all 128 rows of P are in shared memory; TMEM buffer drained
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       // ---- col2im + distortion: 12 x 28 output pixels of this tile's interior
-      for (int p = et; p < 2 * kL3IntH * 2 * kL3IntW; p += 128) {
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int p = et + k * 128;
+        if (p >= kPix) continue;
         const int ry = p / (2 * kL3IntW), rx = p % (2 * kL3IntW);
         const int oy = 2 * hi0 + ry, ox = 2 * wi0 + rx;
         if (oy >= Ho || ox >= Wo) continue;
@@ -182,12 +212,11 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
         if (P.xt_out) { P.xt_out[opix * 3] = v0; P.xt_out[opix * 3 + 1] = v1; P.xt_out[opix * 3 + 2] = v2; }
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         if (oy < P.H && ox < P.W) {
-          const float* xp = P.x + ((static_cast<long long>(img) * P.H + oy) * P.W + ox) * 3;
           const float vv[3] = {v0, v1, v2};
           float gg[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float xv = xp[c];
+            const float xv = xc[k][c];
             const float d = vv[c] - xv;
             acc_s += d * d;
             const float rr = rintf(fminf(fmaxf(vv[c], 0.0f), 1.0f) * 255.0f) - xv * 255.0f;
@@ -198,6 +227,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
         }
         if (P.gx) *reinterpret_cast<uint2*>(P.gx + opix * 4) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, 0.0f));
       }
+      named_bar_sync(1 + grp, 128);           // P buffer may be overwritten by this group's next tile
     }
     flush();
   }
@@ -371,12 +401,296 @@ __global__ void __launch_bounds__(kL3dThreads, 1) k_l3_dgrad(const __grid_consta
 }
 
 // =====================================================================================================
+// dgrad fused with the backward of the inverse GDN that precedes layer 3 (IGDN_2, nn_models.py:59)
+//   g   = dgrad accumulator (d loss / d act_2),  t = g*x/s,  u = t @ gamma^T,  g_x = g*s + x*u      (bf16 out)
+// One persistent CTA per SM: warp 0 issues the MMAs, 4*G worker warps (G = C/64 column groups x 4 TMEM lane quarters)
+// build the im2col A operand of the NEXT tile and run the two point-wise passes of the current one.  gamma (C x C,
+// K-major, SWIZZLE_128B) and the gather weights stay resident in shared memory.  TMEM: accumulator | mixing result.
+// Per tile:  build(t+1) | MMA(t) -> pass 1 (reads x, s; writes t to smem) -> mixing MMA -> pass 2 (stores g_x).
+// =====================================================================================================
+struct alignas(64) L3DgradFusedParams {
+  CUtensorMap gmap;            // gamma [n = C rows][k = C cols] bf16, box {64, C}
+  const __nv_bfloat16* gx;     // [N,Ho,Wo,4]
+  const __nv_bfloat16* wpack;  // [10][C][8]
+  const __nv_bfloat16* x_in;   // saved pre-activation x_2 [N,Hin,Win,C]
+  const __nv_bfloat16* s_in;   // saved sqrt(norm)
+  __nv_bfloat16* out;          // d loss / d x_2
+  int N, Hin, Win, C;
+  int tiles_h, tiles_w, total_tiles;
+};
+
+__device__ __forceinline__ float l3_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float l3_bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ float l3_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// K-groups [G0, G0+NG) (8 bf16 = 16 bytes each) of im2col row `row` = input pixel (tr, tcx) of the tile
+template <int G0, int NG>
+__device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, int tr, int tcx, uint8_t* ab, int row) {
+  constexpr int K0 = G0 * 8, K1 = (G0 + NG) * 8;
+  constexpr int T0 = K0 / 3, T1 = ((K1 - 1) / 3 < 24) ? (K1 - 1) / 3 : 24;
+  uint16_t kv[NG * 8];
+#pragma unroll
+  for (int k = 0; k < NG * 8; ++k) kv[k] = 0;
+#pragma unroll
+  for (int t = T0; t <= T1; ++t) {
+    const int a = t / 5, b = t % 5;
+    const uint2 v = reg[(2 * tr + a) * kRegW + (2 * tcx + b)];
+    const uint16_t ch[3] = {static_cast<uint16_t>(v.x & 0xFFFFu), static_cast<uint16_t>(v.x >> 16),
+                            static_cast<uint16_t>(v.y & 0xFFFFu)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int k = t * 3 + c;
+      if (k >= K0 && k < K1) kv[k - K0] = ch[c];
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    uint4 o;
+    o.x = kv[g * 8 + 0] | (static_cast<uint32_t>(kv[g * 8 + 1]) << 16);
+    o.y = kv[g * 8 + 2] | (static_cast<uint32_t>(kv[g * 8 + 3]) << 16);
+    o.z = kv[g * 8 + 4] | (static_cast<uint32_t>(kv[g * 8 + 5]) << 16);
+    o.w = kv[g * 8 + 6] | (static_cast<uint32_t>(kv[g * 8 + 7]) << 16);
+    *reinterpret_cast<uint4*>(ab + (G0 + g) * 2048 + row * 16) = o;
+  }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
+  constexpr int G = NF / 64;                 // worker groups (column split)
+  constexpr int kWorkers = 128 * G;
+  constexpr int kKc = NF / 64;               // K chunks of the mixing GEMM
+  constexpr int kGammaBytes = kKc * NF * 128;
+  constexpr int kBBytes = 10 * NF * 16;
+  constexpr int kBPad = ((kBBytes + 1023) / 1024) * 1024;
+  constexpr int kAIm = 10 * 128 * 16;        // 20480: im2col A operand (no swizzle)
+  constexpr int kRegBytes = ((kRegH * kRegW * 8 + 127) / 128) * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t gamma_base = base;
+  const uint32_t a2_base = base + kGammaBytes;
+  uint8_t* a2_ptr = smem + kGammaBytes;
+  const uint32_t b_base = a2_base + kKc * 16384;
+  uint8_t* b_ptr = a2_ptr + kKc * 16384;
+  const uint32_t a_base = b_base + kBPad;
+  uint8_t* a_ptr = b_ptr + kBPad;
+  uint8_t* reg_ptr = a_ptr + 2 * kAIm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reg_ptr + 2 * kRegBytes);
+  const uint32_t bar_g = smem_u32(bars);             // gamma loaded
+  const uint32_t bar_afull = bar_g + 8;              // [2] count kWorkers
+  const uint32_t bar_aempty = bar_afull + 16;        // [2] commit
+  const uint32_t bar_tfull = bar_aempty + 16;        // accumulator ready (commit)
+  const uint32_t bar_a2 = bar_tfull + 8;             // mixing operand written + accumulator drained (count kWorkers)
+  const uint32_t bar_nfull = bar_a2 + 8;             // mixing result ready (commit)
+  const uint32_t bar_nempty = bar_nfull + 8;         // mixing result drained (count 4*G)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kBBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(b_ptr)[i] = __ldg(reinterpret_cast<const uint4*>(P.wpack) + i);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&P.gmap);
+      mbar_init(bar_g, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(bar_afull + 8 * b, kWorkers); mbar_init(bar_aempty + 8 * b, 1); }
+      mbar_init(bar_tfull, 1);
+      mbar_init(bar_a2, kWorkers);
+      mbar_init(bar_nfull, 1);
+      mbar_init(bar_nempty, 4 * G);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int tiles_per_img = P.tiles_h * P.tiles_w;
+  const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
+  constexpr uint32_t kNormCol = NF;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_g, kGammaBytes);
+      for (int kc = 0; kc < kKc; ++kc) tma_load_2d(gamma_base + kc * NF * 128, &P.gmap, bar_g, kc * 64, 0);
+      mbar_wait(bar_g, 0);
+      const uint32_t idesc = instr_desc_bf16(128, NF);
+      int it = 0;
+      auto mix = [&](int j) {   // mixing GEMM of tile j: [128 x NF] = t[128 x NF] * gamma^T
+        mbar_wait(bar_a2, j & 1);                     // pass 1 of tile j done: operand in smem, accumulator drained
+        mbar_wait(bar_nempty, (j & 1) ^ 1u);          // pass 2 of tile j-1 has read the previous mixing result
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < kKc; ++kc)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + kNormCol, smem_desc_sw128(a2_base + kc * 16384 + kk * 32),
+                      smem_desc_sw128(gamma_base + kc * NF * 128 + kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
+        umma_commit(bar_nfull);
+      };
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
+        const int buf = it & 1;
+        mbar_wait(bar_afull + 8 * buf, (it >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+          const uint64_t ad = smem_desc_interleave(a_base + buf * kAIm + ks * 2 * 2048, 2048, 128);
+          const uint64_t bd = smem_desc_interleave(b_base + ks * 2 * (NF * 16), NF * 16, 128);
+          umma_bf16(tmem_base, ad, bd, idesc, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_aempty + 8 * buf);
+        umma_commit(bar_tfull);
+      }
+      if (it > 0) mix(it - 1);
+    }
+  } else {
+    const int wt = threadIdx.x - 32;            // worker thread
+    const int grp = (warp - 1) >> 2;            // column group
+    const int q = warp & 3;                     // TMEM lane quarter
+    const int row = q * 32 + lane;              // pixel row for the point-wise passes
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int brow = wt & 127, bpart = wt >> 7; // im2col: row and K part (parts beyond 2 idle)
+
+    auto build = [&](int tile, int it) {
+      const int buf = it & 1;
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
+      uint2* reg = reinterpret_cast<uint2*>(reg_ptr + buf * kRegBytes);
+      mbar_wait(bar_aempty + 8 * buf, ((it >> 1) & 1) ^ 1u);      // MMA of tile it-2 has read A[buf]
+      for (int e = wt; e < kRegH * kRegW; e += kWorkers) {
+        const int ry = e / kRegW, rx = e % kRegW;
+        const int gy = 2 * h0 - 2 + ry, gxx = 2 * w0 - 2 + rx;
+        uint2 v = make_uint2(0u, 0u);
+        if (gy >= 0 && gy < Ho && gxx >= 0 && gxx < Wo)
+          v = __ldg(reinterpret_cast<const uint2*>(P.gx + ((static_cast<long long>(img) * Ho + gy) * Wo + gxx) * 4));
+        reg[e] = v;
+      }
+      named_bar_sync(2, kWorkers);
+      uint8_t* ab = a_ptr + buf * kAIm;
+      const int tr = brow >> 4, tcx = brow & 15;
+      if (G == 3) {
+        if (bpart == 0) l3_build_groups<0, 4>(reg, tr, tcx, ab, brow);
+        else if (bpart == 1) l3_build_groups<4, 3>(reg, tr, tcx, ab, brow);
+        else l3_build_groups<7, 3>(reg, tr, tcx, ab, brow);
+      } else if (G == 2) {
+        if (bpart == 0) l3_build_groups<0, 5>(reg, tr, tcx, ab, brow);
+        else l3_build_groups<5, 5>(reg, tr, tcx, ab, brow);
+      } else {
+        l3_build_groups<0, 10>(reg, tr, tcx, ab, brow);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_afull + 8 * buf);
+    };
+
+    int it = 0;
+    int tile = blockIdx.x;
+    if (tile < P.total_tiles) build(tile, 0);
+    for (; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int i = (tt / P.tiles_w) * 8 + (row >> 4), j = (tt % P.tiles_w) * 16 + (row & 15);
+      const bool valid = (i < P.Hin) && (j < P.Win);
+      const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * NF;
+      // ---- pass 1 (x of both chunks stays in registers for pass 2)
+      uint4 xv[2][4];
+      uint32_t keep[2][16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          xv[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + (grp + h * G) * 32) + u)
+                           : make_uint4(0, 0, 0, 0);
+      mbar_wait(bar_tfull, it & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = grp + h * G;
+        uint4 sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          sv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
+                        : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + c * 32, r);
+        tmem_ld_wait();
+        uint8_t* a2c = a2_ptr + (c >> 1) * 16384;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t a2w[4];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int e = u * 4 + e4;
+            const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[h][u])[e4];
+            const uint32_t sw = reinterpret_cast<const uint32_t*>(&sv[u])[e4];
+            const float x0 = l3_bf16_lo(xw), x1 = l3_bf16_hi(xw), s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
+            keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
+            a2w[e4] = pack_bf16(v0 * x0 * l3_rcp(s0), v1 * x1 * l3_rcp(s1));
+          }
+          *reinterpret_cast<uint4*>(a2c + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(bar_a2);
+      // ---- im2col of the next tile while the mixing GEMM runs
+      const int next = tile + gridDim.x;
+      if (next < P.total_tiles) build(next, it + 1);
+      // ---- pass 2
+      mbar_wait(bar_nfull, it & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = grp + h * G;
+        uint32_t m[32];
+        tmem_ld32(tmem_base + kNormCol + lane_off + c * 32, m);
+        tmem_ld_wait();
+        if (h == 1) {                       // both chunks of the mixing result are in registers: release it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_nempty);
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(P.out + off0 + c * 32);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int e = u * 4 + e4;
+              const uint32_t kw = keep[h][e];
+              const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[h][u])[e4];
+              o[e4] = pack_bf16(l3_bf16_lo(kw) + l3_bf16_lo(xw) * __uint_as_float(m[2 * e]),
+                                l3_bf16_hi(kw) + l3_bf16_hi(xw) * __uint_as_float(m[2 * e + 1]));
+            }
+            op[u] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// =====================================================================================================
 // host
 // =====================================================================================================
 struct L3Tc {
   L3FwdParams F;
   L3DgradParams D;
-  int f_smem, f_grid, d_smem, d_grid;
+  L3DgradFusedParams DF;
+  int f_smem, f_grid, d_smem, d_grid, df_smem;
+  bool fused_ok;
 };
 
 // w_scatter: bf16 [80][C] (row n = (a*5+b)*3+c);  w_gather: bf16 [10][C][8]
@@ -400,8 +714,9 @@ int l3_pack_weights(const float* k3, int C, __nv_bfloat16* w_scatter, __nv_bfloa
   return SGA_OK;
 }
 
-int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const __nv_bfloat16* w_gather, int N, int Hin,
-                 int Win, int C, int H, int W, L3Tc** out) {
+// gamma_bwd_op (optional): bf16 [C][C] K-major operand of the IGDN backward mixing (= gamma in its (in,out) layout)
+int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const __nv_bfloat16* w_gather,
+                 const __nv_bfloat16* gamma_bwd_op, int N, int Hin, int Win, int C, int H, int W, L3Tc** out) {
   SGA_CHECK(C % 64 == 0 && C <= 256, "tcgen05 layer-3 kernels need C %% 64 == 0 and <= 256 (got %d)", C);
   L3Tc* c = new L3Tc();
   memset(c, 0, sizeof(*c));
@@ -440,11 +755,28 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     const int reg_bytes = ((kRegH * kRegW * 8 + 127) / 128) * 128;
     c->d_smem = 1024 + ((b_bytes + 1023) / 1024) * 1024 + 2 * 20480 + 2 * reg_bytes + 256;
     c->d_grid = D.total_tiles < sms ? D.total_tiles : sms;
+    L3DgradFusedParams& DF = c->DF;
+    DF.N = N; DF.Hin = Hin; DF.Win = Win; DF.C = C; DF.wpack = w_gather;
+    DF.tiles_h = D.tiles_h; DF.tiles_w = D.tiles_w; DF.total_tiles = D.total_tiles;
+    c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr;
+    if (c->fused_ok) {
+      const uint64_t gdims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C)};
+      const uint64_t gstr[1] = {static_cast<uint64_t>(C) * 2};
+      const uint32_t gbox[2] = {64, static_cast<uint32_t>(C)};
+      int st = tma_encode_tiled(&DF.gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gamma_bwd_op, gdims, gstr, gbox,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st != SGA_OK) { delete c; return st; }
+    }
+    const int kc = C / 64;
+    c->df_smem = 1024 + kc * C * 128 + kc * 16384 + ((b_bytes + 1023) / 1024) * 1024 + 2 * 20480 + 2 * reg_bytes + 256;
   }
   static bool attr_set = false;
   if (!attr_set) {
     SGA_CUDA(cudaFuncSetAttribute(k_l3_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   *out = c;
@@ -469,6 +801,23 @@ int l3_tc_dgrad(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cuda
   L3DgradParams D = c->D;
   D.gx = gx; D.out = out;
   k_l3_dgrad<<<c->d_grid, kL3dThreads, c->d_smem, st>>>(D);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+bool l3_tc_can_fuse_igdn(const L3Tc* c) { return c->fused_ok; }
+
+int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
+                     __nv_bfloat16* out, cudaStream_t st) {
+  SGA_CHECK(c->fused_ok, "layer-3 dgrad + IGDN backward fusion needs C in {64,128,192} and the gamma operand at create");
+  if (c->DF.total_tiles == 0) return SGA_OK;
+  const int C = c->DF.C;
+  L3DgradFusedParams D = c->DF;
+  D.gx = gx; D.x_in = x_saved; D.s_in = s_saved; D.out = out;
+  const int threads = 32 + 128 * (C / 64);
+  if (C == 192) k_l3_dgrad_igdn<192><<<c->d_grid, threads, c->df_smem, st>>>(D);
+  else if (C == 128) k_l3_dgrad_igdn<128><<<c->d_grid, threads, c->df_smem, st>>>(D);
+  else k_l3_dgrad_igdn<64><<<c->d_grid, threads, c->df_smem, st>>>(D);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
