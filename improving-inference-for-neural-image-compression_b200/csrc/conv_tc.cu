@@ -115,16 +115,22 @@ __device__ __forceinline__ void epilogue_store(const TcParams& P, const uint32_t
     }
   }
   if (P.out_bf16) {
-    uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + off);
 #pragma unroll
-    for (int q = 0; q < NV / 8; ++q)
-      op[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                         pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    for (int q = 0; q < NV / 16; ++q) {
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[q * 16 + 2 * e], v[q * 16 + 2 * e + 1]);
+      st_global_v8(P.out_bf16 + off + q * 16, w);
+    }
   }
   if (P.out_f32) {
-    float4* op = reinterpret_cast<float4*>(P.out_f32 + off);
 #pragma unroll
-    for (int q = 0; q < NV / 4; ++q) op[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    for (int q = 0; q < NV / 8; ++q) {
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(v[q * 8 + e]);
+      st_global_v8(P.out_f32 + off + q * 8, w);
+    }
   }
 }
 
@@ -324,17 +330,21 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       const bool valid = (i < J.Ho) && (j < J.Wo);
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
       // fused backward: the saved x / s of this warp's two chunks are fetched before the accumulator is awaited
-      uint4 xin[(FUSE == 2) ? 2 : 1][4], sin[(FUSE == 2) ? 2 : 1][4];
+      uint32_t xin[(FUSE == 2) ? 2 : 1][16], sin[(FUSE == 2) ? 2 : 1][16];
       if (FUSE == 2) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          const int c = grp + h * G;
+          if (valid) {
+            ld_global_nc_v8(P.x_in + off0 + c * 32, &xin[h][0]);
+            ld_global_nc_v8(P.x_in + off0 + c * 32 + 16, &xin[h][8]);
+            ld_global_nc_v8(P.s_in + off0 + c * 32, &sin[h][0]);
+            ld_global_nc_v8(P.s_in + off0 + c * 32 + 16, &sin[h][8]);
+          } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = grp + h * G;
-            xin[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + c * 32) + u) : make_uint4(0, 0, 0, 0);
-            sin[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
-                              : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+            for (int e = 0; e < 16; ++e) { xin[h][e] = 0u; sin[h][e] = 0x3F803F80u; }
           }
+        }
       }
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
@@ -383,8 +393,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
                 const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);     // the stored (bf16) x is what the mixing sees
                 a2w[e] = pack_bf16(x0 * x0, x1 * x1);
               } else {
-                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
-                const uint32_t sw = reinterpret_cast<const uint32_t*>(&sin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
+                const uint32_t xw = xin[(FUSE == 2) ? h : 0][e];
+                const uint32_t sw = sin[(FUSE == 2) ? h : 0][e];
                 const float x0 = bf16_lo(xw), x1 = bf16_hi(xw), s0 = bf16_lo(sw), s1 = bf16_hi(sw);
                 keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
                 a2w[e] = pack_bf16(v0 * x0 * fast_rcp(s0), v1 * x1 * fast_rcp(s1));
@@ -392,10 +402,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
             }
           }
           if (FUSE == 1 && valid && !(P.dbg & 1)) {
-            uint4* xp = reinterpret_cast<uint4*>(P.xpre_out + off0 + c * 32);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              xp[u] = make_uint4(keep[h][4 * u], keep[h][4 * u + 1], keep[h][4 * u + 2], keep[h][4 * u + 3]);
+            st_global_v8(P.xpre_out + off0 + c * 32, &keep[h][0]);
+            st_global_v8(P.xpre_out + off0 + c * 32 + 16, &keep[h][8]);
           }
           // 32 columns = 4 x 16-byte chunks of K-chunk (c/2), chunk index ((c&1)*4 + u) within the 128-byte row
           uint8_t* a2c = a2_ptr + (c >> 1) * kABytes;
@@ -438,21 +446,19 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
                 o[e] = pack_bf16(bf16_lo(kw) * s0, bf16_hi(kw) * s1);
                 so[e] = pack_bf16(s0, s1);
               } else {
-                const uint32_t xw = reinterpret_cast<const uint32_t*>(&xin[(FUSE == 2) ? h : 0][e >> 2])[e & 3];
+                const uint32_t xw = xin[(FUSE == 2) ? h : 0][e];
                 o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
               }
             }
           }
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + off0 + c * 32);
             if (!(P.dbg & 4)) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+              st_global_v8(P.out_bf16 + off0 + c * 32, &o[0]);
+              st_global_v8(P.out_bf16 + off0 + c * 32 + 16, &o[8]);
             }
             if (FUSE == 1 && !(P.dbg & 2)) {
-              uint4* sp = reinterpret_cast<uint4*>(P.s_out + off0 + c * 32);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) sp[u] = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
+              st_global_v8(P.s_out + off0 + c * 32, &so[0]);
+              st_global_v8(P.s_out + off0 + c * 32 + 16, &so[8]);
             }
           }
         }

@@ -600,24 +600,31 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       const bool valid = (i < P.Hin) && (j < P.Win);
       const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * NF;
       // ---- pass 1 (x of both chunks stays in registers for pass 2)
-      uint4 xv[2][4];
+      uint32_t xv[2][16];
       uint32_t keep[2][16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        if (valid) {
+          ld_global_nc_v8(P.x_in + off0 + (grp + h * G) * 32, &xv[h][0]);
+          ld_global_nc_v8(P.x_in + off0 + (grp + h * G) * 32 + 16, &xv[h][8]);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          xv[h][u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.x_in + off0 + (grp + h * G) * 32) + u)
-                           : make_uint4(0, 0, 0, 0);
+          for (int e = 0; e < 16; ++e) xv[h][e] = 0u;
+        }
+      }
       mbar_wait(bar_tfull, it & 1);
       tcgen05_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = grp + h * G;
-        uint4 sv[4];
+        uint32_t sv[16];
+        if (valid) {
+          ld_global_nc_v8(P.s_in + off0 + c * 32, &sv[0]);
+          ld_global_nc_v8(P.s_in + off0 + c * 32 + 16, &sv[8]);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          sv[u] = valid ? __ldg(reinterpret_cast<const uint4*>(P.s_in + off0 + c * 32) + u)
-                        : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+          for (int e = 0; e < 16; ++e) sv[e] = 0x3F803F80u;
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_off + c * 32, r);
         tmem_ld_wait();
@@ -629,8 +636,8 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
           for (int e4 = 0; e4 < 4; ++e4) {
             const int e = u * 4 + e4;
             const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-            const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[h][u])[e4];
-            const uint32_t sw = reinterpret_cast<const uint32_t*>(&sv[u])[e4];
+            const uint32_t xw = xv[h][e];
+            const uint32_t sw = sv[e];
             const float x0 = l3_bf16_lo(xw), x1 = l3_bf16_hi(xw), s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
             keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
             a2w[e4] = pack_bf16(v0 * x0 * l3_rcp(s0), v1 * x1 * l3_rcp(s1));
@@ -659,19 +666,18 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
           if (lane == 0) mbar_arrive(bar_nempty);
         }
         if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(P.out + off0 + c * 32);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t o[4];
+          for (int u = 0; u < 2; ++u) {
+            uint32_t o[8];
 #pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const int e = u * 4 + e4;
+            for (int e8 = 0; e8 < 8; ++e8) {
+              const int e = u * 8 + e8;
               const uint32_t kw = keep[h][e];
-              const uint32_t xw = reinterpret_cast<const uint32_t*>(&xv[h][u])[e4];
-              o[e4] = pack_bf16(l3_bf16_lo(kw) + l3_bf16_lo(xw) * __uint_as_float(m[2 * e]),
+              const uint32_t xw = xv[h][e];
+              o[e8] = pack_bf16(l3_bf16_lo(kw) + l3_bf16_lo(xw) * __uint_as_float(m[2 * e]),
                                 l3_bf16_hi(kw) + l3_bf16_hi(xw) * __uint_as_float(m[2 * e + 1]));
             }
-            op[u] = make_uint4(o[0], o[1], o[2], o[3]);
+            st_global_v8(P.out + off0 + c * 32 + u * 16, o);
           }
         }
       }
