@@ -50,6 +50,8 @@ struct alignas(64) TcParams {
   CUtensorMap amap[kMaxViews];
   CUtensorMap bmap;
   CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
+  CUtensorMap omap[3][4]; // fused IGDN forward: TMA-store maps of x / s / act for each output phase, box {32, TW, TH, 1}
+  int tma_store;          // fused forward: stage the three outputs in shared memory and store them with TMA
   TcJob job[4];
   Tap taps[kMaxTaps];
   int njobs, N, K, Nn;
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   constexpr int kA2Bytes = (FUSE != 0) ? (NF / 64) * kABytes : 0;
   const uint32_t a2_base = b_base + P.stages * b_bytes;            // fused: A operand of the mixing GEMM
   uint8_t* a2_ptr = smem + P.stages * (kABytes + b_bytes);
-  uint8_t* tail = a2_ptr + kA2Bytes;
+  constexpr int kStgBytes = (FUSE == 1) ? G * 16384 : 0;         // fused fwd: 2 x 8 KB output staging slots per group
+  uint8_t* stg_ptr = a2_ptr + kA2Bytes;
+  uint8_t* tail = stg_ptr + kStgBytes;
   float* s_bias = reinterpret_cast<float*>(tail);                  // 512 floats: bias (or beta for the fused fwd: +256)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512 * sizeof(float));
   // bars: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | a2_full | norm_full | norm_empty
@@ -194,6 +198,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
     for (int v = 0; v < kMaxViews; ++v) tma_prefetch_desc(&P.amap[v]);
     tma_prefetch_desc(&P.bmap);
     if (FUSE != 0) tma_prefetch_desc(&P.gmap);
+    if (FUSE == 1 && P.tma_store)
+      for (int t = 0; t < 3; ++t)
+        for (int jn = 0; jn < P.njobs; ++jn) tma_prefetch_desc(&P.omap[t][jn]);
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -369,6 +376,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       } else {
         // ---------- pass 1: accumulator -> (x | g*s) kept in registers as packed bf16, mixing operand -> smem
         uint32_t keep[2][16];
+        const bool use_tma = (FUSE == 1) && P.tma_store;
+        const bool elected = (((warp - 2) & 3) == 0) && lane == 0;     // issues this group's TMA stores
+        uint8_t* stg = stg_ptr + grp * 16384;
+        const uint32_t stg_u32 = smem_u32(stg);
+        if (use_tma) {                       // the previous stores of this group have finished reading the staging slots
+          if (elected) bulk_wait_read0();
+          named_bar_sync(1 + grp, 128);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = grp + h * G;               // 32-column chunk of the tile owned by this warp in half h
@@ -401,9 +416,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
               }
             }
           }
-          if (FUSE == 1 && valid && !(P.dbg & 1)) {
-            st_global_v8(P.xpre_out + off0 + c * 32, &keep[h][0]);
-            st_global_v8(P.xpre_out + off0 + c * 32 + 16, &keep[h][8]);
+          if (FUSE == 1 && !(P.dbg & 1)) {
+            if (use_tma) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(stg + h * 8192 + sw64_offset(row, u)) =
+                    make_uint4(keep[h][4 * u], keep[h][4 * u + 1], keep[h][4 * u + 2], keep[h][4 * u + 3]);
+            } else if (valid) {
+              st_global_v8(P.xpre_out + off0 + c * 32, &keep[h][0]);
+              st_global_v8(P.xpre_out + off0 + c * 32 + 16, &keep[h][8]);
+            }
           }
           // 32 columns = 4 x 16-byte chunks of K-chunk (c/2), chunk index ((c&1)*4 + u) within the 128-byte row
           uint8_t* a2c = a2_ptr + (c >> 1) * kABytes;
@@ -417,6 +439,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (use_tma && !(P.dbg & 1)) {
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            tma_store_4d(&P.omap[0][tc_.job], stg_u32, tc_.n0 + grp * 32, tc_.w0, tc_.h0, tc_.img);
+            tma_store_4d(&P.omap[0][tc_.job], stg_u32 + 8192, tc_.n0 + (grp + G) * 32, tc_.w0, tc_.h0, tc_.img);
+            bulk_commit_group();
+          }
+        }
         // ---------- pass 2: two halves of the mixing result; this warp owns chunk `grp` of each half
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -451,7 +481,22 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
               }
             }
           }
-          if (valid) {
+          if (use_tma) {
+            if (elected) bulk_wait_read0();
+            named_bar_sync(1 + grp, 128);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(stg + sw64_offset(row, u)) = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
+              *reinterpret_cast<uint4*>(stg + 8192 + sw64_offset(row, u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + grp, 128);
+            if (elected) {
+              if (!(P.dbg & 2)) tma_store_4d(&P.omap[1][tc_.job], stg_u32, tc_.n0 + c * 32, tc_.w0, tc_.h0, tc_.img);
+              if (!(P.dbg & 4)) tma_store_4d(&P.omap[2][tc_.job], stg_u32 + 8192, tc_.n0 + c * 32, tc_.w0, tc_.h0, tc_.img);
+              bulk_commit_group();
+            }
+          } else if (valid) {
             if (!(P.dbg & 4)) {
               st_global_v8(P.out_bf16 + off0 + c * 32, &o[0]);
               st_global_v8(P.out_bf16 + off0 + c * 32 + 16, &o[8]);
@@ -465,6 +510,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       }
       ++it;
     }
+    if (FUSE == 1 && P.tma_store) bulk_wait_all();   // (only the electing threads have groups outstanding)
   }
 
   tcgen05_fence_before();
@@ -521,6 +567,8 @@ struct TcConv {
   int smem_bytes;
   int grid;
   int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
+  const void* omap_ptr[3];   // tensors the forward-fusion store maps were encoded for
+  ConvPlan plan;
 };
 
 static int pick_block_n(int Nn) {
@@ -550,6 +598,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   TcConv* c = new TcConv();
   memset(&c->P, 0, sizeof(c->P));
   c->fuse = fuse;
+  c->plan = plan;
+  c->omap_ptr[0] = c->omap_ptr[1] = c->omap_ptr[2] = nullptr;
   TcParams& P = c->P;
   P.N = g.N; P.K = g.Cin; P.Nn = g.Cout;
   P.block_n = pick_block_n(g.Cout);
@@ -561,6 +611,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     P.mix_at0 = e0 ? atoi(e0) : 6; P.mix_at1 = e1 ? atoi(e1) : 8;
     const char* ed = getenv("SGA_DBG");
     P.dbg = ed ? atoi(ed) : 0;
+    P.tma_store = (fuse == 1 && getenv("SGA_NO_TMA_STORE") == nullptr) ? 1 : 0;
   }
   P.oN = static_cast<long long>(g.Hout) * g.Wout * g.Cout;
   // spatial tile: 128 pixels = TH x TW
@@ -572,7 +623,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.n_spatial = g.N * P.tiles_h * P.tiles_w * P.n_tiles_n;
   const int b_bytes = P.block_n * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
-  const int fixed = 1024 + a2_bytes + 512 * 4 + 256;
+  const int stg_bytes = (fuse == 1) ? (g.Cout / 64) * 16384 : 0;
+  const int fixed = 1024 + a2_bytes + stg_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* es = getenv("SGA_DBG_STAGES")) { const int v = atoi(es); if (v >= 2 && v < stages) stages = v; }
@@ -645,10 +697,30 @@ int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bflo
   return SGA_OK;
 }
 
-int tc_conv_launch_igdn_fwd(const TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
+int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
                             __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st) {
   SGA_CHECK(c->fuse == 1, "conv was not created with forward IGDN fusion");
   if (c->P.n_spatial == 0) return SGA_OK;
+  if (c->P.tma_store) {
+    // (re)encode the store maps when the output tensors change: one 4-D view {C, Wo, Ho, N} per tensor and output phase
+    const void* ptrs[3] = {xpre_out, s_out, act_out};
+    const ConvGeom& g = c->plan.g;
+    for (int t = 0; t < 3; ++t) {
+      if (c->omap_ptr[t] == ptrs[t]) continue;
+      for (int jn = 0; jn < c->P.njobs; ++jn) {
+        const TcJob& J = c->P.job[jn];
+        const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(J.Wo), static_cast<uint64_t>(J.Ho),
+                                  static_cast<uint64_t>(g.N)};
+        const uint64_t strides[3] = {static_cast<uint64_t>(J.oW) * 2, static_cast<uint64_t>(J.oH) * 2,
+                                     static_cast<uint64_t>(c->P.oN) * 2};
+        const uint32_t box[4] = {32, static_cast<uint32_t>(c->P.TW), static_cast<uint32_t>(c->P.TH), 1};
+        SGA_TRY(tma_encode_tiled(&c->P.omap[t][jn], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                 static_cast<const __nv_bfloat16*>(ptrs[t]) + J.out_off, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_64B));
+      }
+      c->omap_ptr[t] = ptrs[t];
+    }
+  }
   TcParams P = c->P;
   P.bias = bias; P.beta = beta; P.xpre_out = xpre_out; P.s_out = s_out; P.out_bf16 = act_out;
   select_kernel(1, P.Nn)<<<c->grid, kernel_threads(1, P.Nn), c->smem_bytes, st>>>(P);

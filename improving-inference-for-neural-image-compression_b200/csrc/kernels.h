@@ -80,7 +80,7 @@ void tc_conv_destroy(TcConv* c);
 int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bfloat16* relu_mask, __nv_bfloat16* out_bf16,
                    float* out_f32, cudaStream_t st);
 // x = acc + bias; s = sqrt(beta + x^2 @ gamma); act = x*s  -- all three stored as bf16
-int tc_conv_launch_igdn_fwd(const TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
+int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
                             __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st);
 // g = acc; g_x = g*s + x*((g*x/s) @ gamma^T) stored as bf16
 int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,

@@ -403,17 +403,18 @@ __global__ void __launch_bounds__(kL3dThreads, 1) k_l3_dgrad(const __grid_consta
 // =====================================================================================================
 // dgrad fused with the backward of the inverse GDN that precedes layer 3 (IGDN_2, nn_models.py:59)
 //   g   = dgrad accumulator (d loss / d act_2),  t = g*x/s,  u = t @ gamma^T,  g_x = g*s + x*u      (bf16 out)
-// One persistent CTA per SM: warp 0 issues the MMAs, 4*G worker warps (G = C/64 column groups x 4 TMEM lane quarters)
-// build the im2col A operand of the NEXT tile and run the two point-wise passes of the current one.  gamma (C x C,
-// K-major, SWIZZLE_128B) and the gather weights stay resident in shared memory.  TMEM: accumulator | mixing result.
-// Per tile:  build(t+1) | MMA(t) -> pass 1 (reads x, s; writes t to smem) -> mixing MMA -> pass 2 (stores g_x).
+// One persistent CTA per SM: warp 0 issues the MMAs, warp 1 streams the saved x / s tiles in with TMA (the x tile lands
+// in the buffer that pass 1 then overwrites in place with the mixing operand t), 4*G worker warps (G = C/64 column
+// groups x 4 TMEM lane quarters) build the im2col A operand of the NEXT tile from a gradient patch they fetched one tile
+// ahead and run the two point-wise passes of the current one.  gamma (C x C, K-major, SWIZZLE_128B) and the gather
+// weights stay resident in shared memory.  TMEM: accumulator | mixing result.
+// Per tile:  MMA(t) -> pass 1 (g, x, s -> t) -> mixing MMA || build(t+1), TMA x/s(t+1) -> pass 2 (stores g_x).
 // =====================================================================================================
 struct alignas(64) L3DgradFusedParams {
   CUtensorMap gmap;            // gamma [n = C rows][k = C cols] bf16, box {64, C}
+  CUtensorMap xmap, smap;      // saved x_2 / s_2 [N,Hin,Win,C] bf16, box {64, 16, 8, 1}
   const __nv_bfloat16* gx;     // [N,Ho,Wo,4]
   const __nv_bfloat16* wpack;  // [10][C][8]
-  const __nv_bfloat16* x_in;   // saved pre-activation x_2 [N,Hin,Win,C]
-  const __nv_bfloat16* s_in;   // saved sqrt(norm)
   __nv_bfloat16* out;          // d loss / d x_2
   int N, Hin, Win, C;
   int tiles_h, tiles_w, total_tiles;
@@ -459,11 +460,12 @@ __device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, i
 }
 
 template <int NF>
-__global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
+__global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
   constexpr int G = NF / 64;                 // worker groups (column split)
   constexpr int kWorkers = 128 * G;
   constexpr int kKc = NF / 64;               // K chunks of the mixing GEMM
   constexpr int kGammaBytes = kKc * NF * 128;
+  constexpr int kTileBytes = kKc * 16384;    // one [128 px x NF] bf16 tile in SWIZZLE_128B K-major chunks
   constexpr int kBBytes = 10 * NF * 16;
   constexpr int kBPad = ((kBBytes + 1023) / 1024) * 1024;
   constexpr int kAIm = 10 * 128 * 16;        // 20480: im2col A operand (no swizzle)
@@ -472,23 +474,28 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
+  // gamma | x tile (becomes the mixing operand t in place) | s tile | gather weights | im2col A | gradient patch | barriers
   const uint32_t gamma_base = base;
   const uint32_t a2_base = base + kGammaBytes;
   uint8_t* a2_ptr = smem + kGammaBytes;
-  const uint32_t b_base = a2_base + kKc * 16384;
-  uint8_t* b_ptr = a2_ptr + kKc * 16384;
+  const uint32_t s_base = a2_base + kTileBytes;
+  uint8_t* s_ptr = a2_ptr + kTileBytes;
+  const uint32_t b_base = s_base + kTileBytes;
+  uint8_t* b_ptr = s_ptr + kTileBytes;
   const uint32_t a_base = b_base + kBPad;
   uint8_t* a_ptr = b_ptr + kBPad;
-  uint8_t* reg_ptr = a_ptr + 2 * kAIm;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reg_ptr + 2 * kRegBytes);
-  const uint32_t bar_g = smem_u32(bars);             // gamma loaded
-  const uint32_t bar_afull = bar_g + 8;              // [2] count kWorkers
-  const uint32_t bar_aempty = bar_afull + 16;        // [2] commit
-  const uint32_t bar_tfull = bar_aempty + 16;        // accumulator ready (commit)
-  const uint32_t bar_a2 = bar_tfull + 8;             // mixing operand written + accumulator drained (count kWorkers)
-  const uint32_t bar_nfull = bar_a2 + 8;             // mixing result ready (commit)
+  uint8_t* reg_ptr = a_ptr + kAIm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reg_ptr + kRegBytes);
+  const uint32_t bar_g = smem_u32(bars);             // gamma loaded (tx)
+  const uint32_t bar_afull = bar_g + 8;              // im2col operand built (count kWorkers)
+  const uint32_t bar_aempty = bar_afull + 8;         // ... consumed (commit)
+  const uint32_t bar_tfull = bar_aempty + 8;         // accumulator ready (commit)
+  const uint32_t bar_a2 = bar_tfull + 8;             // pass 1 done: t in smem, accumulator + s tile drained (count kWorkers)
+  const uint32_t bar_nfull = bar_a2 + 8;             // mixing result ready (commit); also: x/t tile free again
   const uint32_t bar_nempty = bar_nfull + 8;         // mixing result drained (count 4*G)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t bar_xfull = bar_nempty + 8;         // x tile landed (tx)
+  const uint32_t bar_sfull = bar_xfull + 8;          // s tile landed (tx)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kBBytes / 16; i += blockDim.x)
@@ -497,12 +504,17 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&P.gmap);
+      tma_prefetch_desc(&P.xmap);
+      tma_prefetch_desc(&P.smap);
       mbar_init(bar_g, 1);
-      for (int b = 0; b < 2; ++b) { mbar_init(bar_afull + 8 * b, kWorkers); mbar_init(bar_aempty + 8 * b, 1); }
+      mbar_init(bar_afull, kWorkers);
+      mbar_init(bar_aempty, 1);
       mbar_init(bar_tfull, 1);
       mbar_init(bar_a2, kWorkers);
       mbar_init(bar_nfull, 1);
       mbar_init(bar_nempty, 4 * G);
+      mbar_init(bar_xfull, 1);
+      mbar_init(bar_sfull, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -518,6 +530,7 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   constexpr uint32_t kNormCol = NF;
 
   if (warp == 0) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_g, kGammaBytes);
       for (int kc = 0; kc < kKc; ++kc) tma_load_2d(gamma_base + kc * NF * 128, &P.gmap, bar_g, kc * 64, 0);
@@ -538,97 +551,118 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       };
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
-        const int buf = it & 1;
-        mbar_wait(bar_afull + 8 * buf, (it >> 1) & 1);
+        mbar_wait(bar_afull, it & 1);
         tcgen05_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks) {
-          const uint64_t ad = smem_desc_interleave(a_base + buf * kAIm + ks * 2 * 2048, 2048, 128);
+          const uint64_t ad = smem_desc_interleave(a_base + ks * 2 * 2048, 2048, 128);
           const uint64_t bd = smem_desc_interleave(b_base + ks * 2 * (NF * 16), NF * 16, 128);
           umma_bf16(tmem_base, ad, bd, idesc, ks != 0 ? 1u : 0u);
         }
-        umma_commit(bar_aempty + 8 * buf);
+        umma_commit(bar_aempty);
         umma_commit(bar_tfull);
       }
       if (it > 0) mix(it - 1);
     }
+  } else if (warp == 1) {
+    // ===================== TMA producer: saved x and s tiles =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
+        if (it > 0) mbar_wait(bar_a2, (it - 1) & 1);          // pass 1 of the previous tile has consumed its s tile
+        mbar_arrive_expect_tx(bar_sfull, kTileBytes);
+        for (int kc = 0; kc < kKc; ++kc) tma_load_4d(s_base + kc * 16384, &P.smap, bar_sfull, kc * 64, w0, h0, img);
+        if (it > 0) mbar_wait(bar_nfull, (it - 1) & 1);       // the mixing GEMM has finished reading t of the previous tile
+        mbar_arrive_expect_tx(bar_xfull, kTileBytes);
+        for (int kc = 0; kc < kKc; ++kc) tma_load_4d(a2_base + kc * 16384, &P.xmap, bar_xfull, kc * 64, w0, h0, img);
+      }
+    }
   } else {
-    const int wt = threadIdx.x - 32;            // worker thread
-    const int grp = (warp - 1) >> 2;            // column group
+    // ===================== workers =====================
+    const int wt = threadIdx.x - 64;            // worker thread
+    const int grp = (warp - 2) >> 2;            // column group
     const int q = warp & 3;                     // TMEM lane quarter
     const int row = q * 32 + lane;              // pixel row for the point-wise passes
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const int brow = wt & 127, bpart = wt >> 7; // im2col: row and K part (parts beyond 2 idle)
+    const int brow = wt & 127, bpart = wt >> 7; // im2col: row and K part
+    constexpr int kPatchPer = (kRegH * kRegW + kWorkers - 1) / kWorkers;
+    uint2 pre[kPatchPer];                       // gradient patch entries of the tile built next, fetched one tile ahead
 
-    auto build = [&](int tile, int it) {
-      const int buf = it & 1;
+    auto fetch_patch = [&](int tile) {
       const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
       const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
-      uint2* reg = reinterpret_cast<uint2*>(reg_ptr + buf * kRegBytes);
-      mbar_wait(bar_aempty + 8 * buf, ((it >> 1) & 1) ^ 1u);      // MMA of tile it-2 has read A[buf]
-      for (int e = wt; e < kRegH * kRegW; e += kWorkers) {
+#pragma unroll
+      for (int k = 0; k < kPatchPer; ++k) {
+        const int e = wt + k * kWorkers;
         const int ry = e / kRegW, rx = e % kRegW;
         const int gy = 2 * h0 - 2 + ry, gxx = 2 * w0 - 2 + rx;
-        uint2 v = make_uint2(0u, 0u);
-        if (gy >= 0 && gy < Ho && gxx >= 0 && gxx < Wo)
-          v = __ldg(reinterpret_cast<const uint2*>(P.gx + ((static_cast<long long>(img) * Ho + gy) * Wo + gxx) * 4));
-        reg[e] = v;
+        pre[k] = make_uint2(0u, 0u);
+        if (e < kRegH * kRegW && gy >= 0 && gy < Ho && gxx >= 0 && gxx < Wo)
+          pre[k] = __ldg(reinterpret_cast<const uint2*>(P.gx + ((static_cast<long long>(img) * Ho + gy) * Wo + gxx) * 4));
+      }
+    };
+    auto build = [&](int it) {                  // im2col operand of tile `it` from the prefetched patch
+      uint2* reg = reinterpret_cast<uint2*>(reg_ptr);
+      if (it > 0) mbar_wait(bar_aempty, (it - 1) & 1);            // MMA of the previous tile has read the operand
+#pragma unroll
+      for (int k = 0; k < kPatchPer; ++k) {
+        const int e = wt + k * kWorkers;
+        if (e < kRegH * kRegW) reg[e] = pre[k];
       }
       named_bar_sync(2, kWorkers);
-      uint8_t* ab = a_ptr + buf * kAIm;
       const int tr = brow >> 4, tcx = brow & 15;
       if (G == 3) {
-        if (bpart == 0) l3_build_groups<0, 4>(reg, tr, tcx, ab, brow);
-        else if (bpart == 1) l3_build_groups<4, 3>(reg, tr, tcx, ab, brow);
-        else l3_build_groups<7, 3>(reg, tr, tcx, ab, brow);
+        if (bpart == 0) l3_build_groups<0, 4>(reg, tr, tcx, a_ptr, brow);
+        else if (bpart == 1) l3_build_groups<4, 3>(reg, tr, tcx, a_ptr, brow);
+        else l3_build_groups<7, 3>(reg, tr, tcx, a_ptr, brow);
       } else if (G == 2) {
-        if (bpart == 0) l3_build_groups<0, 5>(reg, tr, tcx, ab, brow);
-        else l3_build_groups<5, 5>(reg, tr, tcx, ab, brow);
+        if (bpart == 0) l3_build_groups<0, 5>(reg, tr, tcx, a_ptr, brow);
+        else l3_build_groups<5, 5>(reg, tr, tcx, a_ptr, brow);
       } else {
-        l3_build_groups<0, 10>(reg, tr, tcx, ab, brow);
+        l3_build_groups<0, 10>(reg, tr, tcx, a_ptr, brow);
       }
       fence_proxy_async_smem();
-      mbar_arrive(bar_afull + 8 * buf);
+      mbar_arrive(bar_afull);
+      named_bar_sync(2, kWorkers);              // the patch may be overwritten by the next build
     };
 
     int it = 0;
     int tile = blockIdx.x;
-    if (tile < P.total_tiles) build(tile, 0);
+    if (tile < P.total_tiles) {
+      fetch_patch(tile);
+      build(0);
+      if (tile + static_cast<int>(gridDim.x) < P.total_tiles) fetch_patch(tile + gridDim.x);
+    }
     for (; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
       const int i = (tt / P.tiles_w) * 8 + (row >> 4), j = (tt % P.tiles_w) * 16 + (row & 15);
       const bool valid = (i < P.Hin) && (j < P.Win);
       const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * NF;
-      // ---- pass 1 (x of both chunks stays in registers for pass 2)
-      uint32_t xv[2][16];
-      uint32_t keep[2][16];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (valid) {
-          ld_global_nc_v8(P.x_in + off0 + (grp + h * G) * 32, &xv[h][0]);
-          ld_global_nc_v8(P.x_in + off0 + (grp + h * G) * 32 + 16, &xv[h][8]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) xv[h][e] = 0u;
-        }
-      }
+      // ---- pass 1: g (TMEM), x and s (smem)  ->  t in place of x, g*s and x kept as packed bf16
+      uint32_t keep[2][16], xk[2][16];
+      mbar_wait(bar_sfull, it & 1);
+      mbar_wait(bar_xfull, it & 1);
       mbar_wait(bar_tfull, it & 1);
       tcgen05_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = grp + h * G;
-        uint32_t sv[16];
-        if (valid) {
-          ld_global_nc_v8(P.s_in + off0 + c * 32, &sv[0]);
-          ld_global_nc_v8(P.s_in + off0 + c * 32 + 16, &sv[8]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sv[e] = 0x3F803F80u;
-        }
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_off + c * 32, r);
+        uint8_t* xc = a2_ptr + (c >> 1) * 16384;
+        const uint8_t* sc = s_ptr + (c >> 1) * 16384;
+        uint32_t sv[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t o = sw128_offset(row, (c & 1) * 4 + u);
+          const uint4 xq = *reinterpret_cast<const uint4*>(xc + o);
+          const uint4 sq = *reinterpret_cast<const uint4*>(sc + o);
+          xk[h][4 * u] = xq.x; xk[h][4 * u + 1] = xq.y; xk[h][4 * u + 2] = xq.z; xk[h][4 * u + 3] = xq.w;
+          sv[4 * u] = sq.x; sv[4 * u + 1] = sq.y; sv[4 * u + 2] = sq.z; sv[4 * u + 3] = sq.w;
+        }
         tmem_ld_wait();
-        uint8_t* a2c = a2_ptr + (c >> 1) * 16384;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint32_t a2w[4];
@@ -636,21 +670,24 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
           for (int e4 = 0; e4 < 4; ++e4) {
             const int e = u * 4 + e4;
             const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-            const uint32_t xw = xv[h][e];
-            const uint32_t sw = sv[e];
+            const uint32_t xw = xk[h][e];
+            const uint32_t sw = valid ? sv[e] : 0x3F803F80u;     // out-of-image rows are zero-filled by TMA: s = 1
             const float x0 = l3_bf16_lo(xw), x1 = l3_bf16_hi(xw), s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
             keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
             a2w[e4] = pack_bf16(v0 * x0 * l3_rcp(s0), v1 * x1 * l3_rcp(s1));
           }
-          *reinterpret_cast<uint4*>(a2c + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
+          *reinterpret_cast<uint4*>(xc + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
         }
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(bar_a2);
-      // ---- im2col of the next tile while the mixing GEMM runs
+      // ---- im2col of the next tile while the mixing GEMM runs; then fetch the patch of the tile after it
       const int next = tile + gridDim.x;
-      if (next < P.total_tiles) build(next, it + 1);
+      if (next < P.total_tiles) {
+        build(it + 1);
+        if (next + static_cast<int>(gridDim.x) < P.total_tiles) fetch_patch(next + gridDim.x);
+      }
       // ---- pass 2
       mbar_wait(bar_nfull, it & 1);
       tcgen05_fence_after();
@@ -673,7 +710,7 @@ __global__ void __launch_bounds__(32 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
             for (int e8 = 0; e8 < 8; ++e8) {
               const int e = u * 8 + e8;
               const uint32_t kw = keep[h][e];
-              const uint32_t xw = xv[h][e];
+              const uint32_t xw = xk[h][e];
               o[e8] = pack_bf16(l3_bf16_lo(kw) + l3_bf16_lo(xw) * __uint_as_float(m[2 * e]),
                                 l3_bf16_hi(kw) + l3_bf16_hi(xw) * __uint_as_float(m[2 * e + 1]));
             }
@@ -722,7 +759,8 @@ int l3_pack_weights(const float* k3, int C, __nv_bfloat16* w_scatter, __nv_bfloa
 
 // gamma_bwd_op (optional): bf16 [C][C] K-major operand of the IGDN backward mixing (= gamma in its (in,out) layout)
 int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const __nv_bfloat16* w_gather,
-                 const __nv_bfloat16* gamma_bwd_op, int N, int Hin, int Win, int C, int H, int W, L3Tc** out) {
+                 const __nv_bfloat16* gamma_bwd_op, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved, int N,
+                 int Hin, int Win, int C, int H, int W, L3Tc** out) {
   SGA_CHECK(C % 64 == 0 && C <= 256, "tcgen05 layer-3 kernels need C %% 64 == 0 and <= 256 (got %d)", C);
   L3Tc* c = new L3Tc();
   memset(c, 0, sizeof(*c));
@@ -764,8 +802,19 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     L3DgradFusedParams& DF = c->DF;
     DF.N = N; DF.Hin = Hin; DF.Win = Win; DF.C = C; DF.wpack = w_gather;
     DF.tiles_h = D.tiles_h; DF.tiles_w = D.tiles_w; DF.total_tiles = D.total_tiles;
-    c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr;
+    c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr && x_saved != nullptr && s_saved != nullptr;
     if (c->fused_ok) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                                static_cast<uint64_t>(N)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Win) * C * 2,
+                                   static_cast<uint64_t>(Hin) * Win * C * 2};
+      const uint32_t box[4] = {64, 16, 8, 1};
+      int stx = tma_encode_tiled(&DF.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x_saved, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_128B);
+      if (stx == SGA_OK)
+        stx = tma_encode_tiled(&DF.smap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s_saved, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+      if (stx != SGA_OK) { delete c; return stx; }
       const uint64_t gdims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C)};
       const uint64_t gstr[1] = {static_cast<uint64_t>(C) * 2};
       const uint32_t gbox[2] = {64, static_cast<uint32_t>(C)};
@@ -774,7 +823,7 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
       if (st != SGA_OK) { delete c; return st; }
     }
     const int kc = C / 64;
-    c->df_smem = 1024 + kc * C * 128 + kc * 16384 + ((b_bytes + 1023) / 1024) * 1024 + 2 * 20480 + 2 * reg_bytes + 256;
+    c->df_smem = 1024 + kc * C * 128 + 2 * kc * 16384 + ((b_bytes + 1023) / 1024) * 1024 + 20480 + reg_bytes + 256;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -813,14 +862,13 @@ int l3_tc_dgrad(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cuda
 
 bool l3_tc_can_fuse_igdn(const L3Tc* c) { return c->fused_ok; }
 
-int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
-                     __nv_bfloat16* out, cudaStream_t st) {
+int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cudaStream_t st) {
   SGA_CHECK(c->fused_ok, "layer-3 dgrad + IGDN backward fusion needs C in {64,128,192} and the gamma operand at create");
   if (c->DF.total_tiles == 0) return SGA_OK;
   const int C = c->DF.C;
   L3DgradFusedParams D = c->DF;
-  D.gx = gx; D.x_in = x_saved; D.s_in = s_saved; D.out = out;
-  const int threads = 32 + 128 * (C / 64);
+  D.gx = gx; D.out = out;
+  const int threads = 64 + 128 * (C / 64);
   if (C == 192) k_l3_dgrad_igdn<192><<<c->d_grid, threads, c->df_smem, st>>>(D);
   else if (C == 128) k_l3_dgrad_igdn<128><<<c->d_grid, threads, c->df_smem, st>>>(D);
   else k_l3_dgrad_igdn<64><<<c->d_grid, threads, c->df_smem, st>>>(D);
