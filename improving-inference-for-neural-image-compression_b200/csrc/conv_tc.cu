@@ -12,7 +12,13 @@
 // per TMEM lane quarter; the groups split the accumulator columns) -- the epilogue must finish a tile faster than the
 // tensor pipe does (~6 us for a 128x192 tile of the widest layer), which 4 warps cannot do for the fused variants.
 // Persistent CTAs (one per SM); the TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs
-// of tile i+1.  Tiles are issued in waves of gridDim.x spatial tiles per output phase, so the 4 phases of a transposed
+// of tile i+1.
+// CTA pairs (template CG = 2, the default): the kernel is L2->SM bandwidth bound when every CTA streams its own A and B
+// tiles (40 KB per 64-wide K chunk at N = 192, i.e. ~100 B/clk/SM at the tensor rate), so two CTAs of one TPC run as a
+// cluster and issue tcgen05.mma.cta_group::2 (M = 256): each CTA loads the A tile of its own 128 pixels and only HALF of
+// the weight tile, the tensor core reads the other half from the peer's shared memory.  Only the leader (cluster rank 0)
+// issues MMAs; both producers signal the leader's "full" barrier, the MMA commits are multicast to both CTAs' barriers,
+// and the peer's epilogue warps arrive on the leader's barriers through shared::cluster addresses.  Tiles are issued in waves of gridDim.x spatial tiles per output phase, so the 4 phases of a transposed
 // conv re-read their (shared) input from L2 instead of HBM and every CTA gets the same mix of 9/6/6/4-tap tiles.
 //
 // Fused IGDN (template FUSE): the CxC channel mixing of tfc.GDN(inverse=True) (nn_models.py:51,55,59) runs as a second
@@ -58,6 +64,8 @@ struct alignas(64) TcParams {
   int block_n, n_tiles_n, kchunks, stages;
   int TH, TW, tiles_h, tiles_w;
   int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
+  int n_sp;               // spatial tiles per job and N tile = N * tiles_h * tiles_w
+  int n_sp_pairs;         // CTA-pair mode: ceil(n_sp / 2)
   int relu;
   int dbg;                // debug/timing experiments only (env SGA_DBG): 1 skip xpre store, 2 skip s store, 4 skip out store
   int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
@@ -77,19 +85,38 @@ struct alignas(64) TcParams {
 struct TileCoord { int job, img, h0, w0, n0; };
 
 // slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G)
-__device__ __forceinline__ bool decode_slot(const TcParams& P, int k, TileCoord& tc_) {
+// CG = 2: the unit is a pair of horizontally adjacent spatial tiles sharing the N tile; a pair whose second tile does
+// not exist still runs it with img = N (TMA zero-fills the loads, nothing is stored).
+template <int CG>
+__device__ __forceinline__ bool decode_slot(const TcParams& P, int k, uint32_t rank, TileCoord& tc_) {
   const int jb = k % P.njobs;
-  int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-  if (t >= P.n_spatial) return false;
-  const int nt = t % P.n_tiles_n; t /= P.n_tiles_n;
-  const int tw = t % P.tiles_w; t /= P.tiles_w;
-  const int th = t % P.tiles_h;
-  const int img = t / P.tiles_h;
+  int sp, nt;
+  if (CG == 1) {
+    int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+    if (t >= P.n_spatial) return false;
+    nt = t % P.n_tiles_n;
+    sp = t / P.n_tiles_n;
+  } else {
+    const int u = (k / P.njobs) * static_cast<int>(gridDim.x >> 1) + static_cast<int>(blockIdx.x >> 1);
+    if (u >= P.n_sp_pairs * P.n_tiles_n) return false;
+    nt = u / P.n_sp_pairs;
+    sp = (u % P.n_sp_pairs) * 2 + static_cast<int>(rank);
+  }
+  if (sp >= P.n_sp) {
+    tc_ = TileCoord{jb, P.N, 0, 0, nt * P.block_n};
+    return true;
+  }
+  const int tw = sp % P.tiles_w; sp /= P.tiles_w;
+  const int th = sp % P.tiles_h;
+  const int img = sp / P.tiles_h;
   tc_ = TileCoord{jb, img, th * P.TH, tw * P.TW, nt * P.block_n};
   return true;
 }
+template <int CG>
 __device__ __forceinline__ int num_waves(const TcParams& P) {
-  return ((P.n_spatial + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) * P.njobs;
+  const int units = (CG == 1) ? P.n_spatial : P.n_sp_pairs * P.n_tiles_n;
+  const int g = static_cast<int>(gridDim.x) / CG;
+  return ((units + g - 1) / g) * P.njobs;
 }
 
 template <int NV>
@@ -154,14 +181,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // G = number of epilogue warp groups (4 warps each: one per TMEM lane quarter); the groups split the accumulator
 // columns in 32-column chunks.  Fused variants use G = NF/64, so every epilogue warp owns exactly one chunk in each
 // half of the tile (chunk grp of half 0, chunk grp of half 1) and keeps its point-wise state in registers.
-template <int FUSE, int NF, int G>
+// CG = CTAs per MMA (1, or 2 = CTA pair launched as a cluster of two).
+template <int FUSE, int NF, int G, int CG>
 __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_constant__ TcParams P) {
   static_assert(FUSE == 0 || G * 64 == NF, "fused variants: one 32-column chunk per warp and half");
+  static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int b_bytes = P.block_n * kBlockK * 2;
+  const int b_bytes = (P.block_n / CG) * kBlockK * 2;   // this CTA's share of the weight tile
   const uint32_t a_base = base;
   const uint32_t b_base = base + P.stages * kABytes;
   constexpr int kA2Bytes = (FUSE != 0) ? (NF / 64) * kABytes : 0;
@@ -181,6 +212,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   const uint32_t bar_nfull = bar_a2 + 8;
   const uint32_t bar_nempty = bar_nfull + 8;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 7);
+  // barriers the peer CTA of a pair arrives on live in the leader: shared::cluster addresses (CG = 1: the local ones)
+  const uint32_t lead_full = (CG == 2) ? mapa_shared(bar_full, 0) : bar_full;
+  const uint32_t lead_tempty = (CG == 2) ? mapa_shared(bar_tempty, 0) : bar_tempty;
+  const uint32_t lead_a2 = (CG == 2) ? mapa_shared(bar_a2, 0) : bar_a2;
+  const uint32_t lead_nempty = (CG == 2) ? mapa_shared(bar_nempty, 0) : bar_nempty;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kAccStride = (FUSE != 0) ? NF : 256;               // TMEM columns between the two accumulators
@@ -207,97 +243,141 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4 * G);
+      mbar_init(bar_tempty + 8 * b, 4 * G * CG);
     }
-    mbar_init(bar_a2, 128 * G);
+    mbar_init(bar_a2, 128 * G * CG);
     mbar_init(bar_nfull, 1);
-    mbar_init(bar_nempty, 4 * G);
+    mbar_init(bar_nempty, 4 * G * CG);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(s_tmem), kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_cg2(smem_u32(s_tmem), kTmemCols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(smem_u32(s_tmem), kTmemCols); tmem_relinquish(); }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int nwaves = num_waves(P);
+  const int nwaves = num_waves<CG>(P);
+  // wait on a barrier the peer CTA arrives on / arrive on a leader barrier
+  auto wait_x = [](uint32_t bar, uint32_t parity) { if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
+  auto arrive_lead = [](uint32_t local_bar, uint32_t lead_bar) { if (CG == 2) mbar_arrive_cluster(lead_bar); else mbar_arrive(local_bar); };
+  // SGA_DBG & 8: per-role wait-cycle accounting, printed by the first and one middle CTA (development aid)
+  const bool dbg_t = (P.dbg & 8) != 0;
+  long long dbg_w[4] = {0, 0, 0, 0};
+  const long long dbg_t0 = dbg_t ? clock64() : 0;
+  unsigned long long dbg_g0 = 0;
+  if (dbg_t) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+#define SGA_TIMED(slot, stmt)                                  \
+  do {                                                         \
+    if (dbg_t) { const long long _c = clock64(); stmt; dbg_w[slot] += clock64() - _c; } else { stmt; } \
+  } while (0)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / coordinates in uniform registers);
+    // one elected lane issues the copies.  A single-lane loop costs ~350 clk of dependent-issue latency per K chunk,
+    // which is as long as the 4 MMAs that consume the chunk.
+    {
       int stage = 0;
       uint32_t phase = 0;
       auto mix_loads = [&](int h) {   // gamma rows [h*N/2, +N/2), all K chunks, through the regular B stages
         for (int kc = 0; kc < NF / 64; ++kc) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, kNHalf * 128);
-          tma_load_2d(b_base + stage * b_bytes, &P.gmap, bar_full + 8 * stage, kc * kBlockK, h * kNHalf);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, kNHalf * 128);
+            if (CG == 2)
+              tma_load_2d_cg2(b_base + stage * b_bytes, &P.gmap, lead_full + 8 * stage, kc * kBlockK,
+                              h * kNHalf + static_cast<int>(rank) * (kNHalf / 2));
+            else
+              tma_load_2d(b_base + stage * b_bytes, &P.gmap, bar_full + 8 * stage, kc * kBlockK, h * kNHalf);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
       };
       bool pending = false;           // a finished tile whose mixing GEMM has not been issued yet
+      const uint32_t stage_tx = static_cast<uint32_t>(CG * (kABytes + b_bytes));
+      const int b_row_off = static_cast<int>(rank) * (P.block_n / 2);
       for (int w = 0; w < nwaves; ++w) {
         TileCoord tc_;
-        if (!decode_slot(P, w, tc_)) continue;
+        if (!decode_slot<CG>(P, w, rank, tc_)) continue;
         const TcJob& J = P.job[tc_.job];
         const int nk = J.ntaps * P.kchunks;
         const int ins0 = (P.mix_at0 * nk) / 8, ins1 = (P.mix_at1 * nk) / 8 < nk ? (P.mix_at1 * nk) / 8 : nk - 1;
         int k = 0;
         for (int t = 0; t < J.ntaps; ++t) {
           const Tap tap = P.taps[J.tap_begin + t];
+          const CUtensorMap* am = &P.amap[tap.view];
+          const int ax = tc_.w0 + tap.dx, ay = tc_.h0 + tap.dy, brow = tap.widx * P.Nn + tc_.n0 + (CG == 2 ? b_row_off : 0);
           for (int kc = 0; kc < P.kchunks; ++kc, ++k) {
             if (FUSE != 0 && pending) {
               if (k == ins0) mix_loads(0);
               if (k == ins1) mix_loads(1);
             }
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, kABytes + b_bytes);
-            tma_load_4d(a_base + stage * kABytes, &P.amap[tap.view], bar_full + 8 * stage, kc * kBlockK,
-                        tc_.w0 + tap.dx, tc_.h0 + tap.dy, tc_.img);
-            tma_load_2d(b_base + stage * b_bytes, &P.bmap, bar_full + 8 * stage, kc * kBlockK,
-                        tap.widx * P.Nn + tc_.n0);
+            SGA_TIMED(0, mbar_wait(bar_empty + 8 * stage, phase ^ 1u));
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_tx);
+              if (CG == 2) {
+                tma_load_4d_cg2(a_base + stage * kABytes, am, lead_full + 8 * stage, kc * kBlockK, ax, ay, tc_.img);
+                tma_load_2d_cg2(b_base + stage * b_bytes, &P.bmap, lead_full + 8 * stage, kc * kBlockK, brow);
+              } else {
+                tma_load_4d(a_base + stage * kABytes, am, bar_full + 8 * stage, kc * kBlockK, ax, ay, tc_.img);
+                tma_load_2d(b_base + stage * b_bytes, &P.bmap, bar_full + 8 * stage, kc * kBlockK, brow);
+              }
+            }
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
         }
         pending = true;
       }
       if (FUSE != 0 && pending) { mix_loads(0); mix_loads(1); }
+      if (dbg_t && lane == 0 && (blockIdx.x < 2 || blockIdx.x == 74))
+        printf("dbg cta %d producer: total %lld wait_empty %lld\n", blockIdx.x, clock64() - dbg_t0, dbg_w[0]);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc_bf16(kBlockM, P.block_n);
-      const uint32_t idesc_mix = instr_desc_bf16(kBlockM, (FUSE != 0) ? kNHalf : 16);
+    // Warp-uniform loop, one elected lane issues the MMAs and commits (tcgen05.commit tracks the issuing thread's MMAs:
+    // elect.sync on a converged warp always picks the same lane).
+    if (leader) {
+      const uint32_t idesc = instr_desc_bf16(kBlockM * CG, P.block_n);
+      const uint32_t idesc_mix = instr_desc_bf16(kBlockM * CG, (FUSE != 0) ? kNHalf : 16);
+      auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+        if (CG == 2) umma_bf16_cg2(d, ad, bd, id, acc); else umma_bf16(d, ad, bd, id, acc);
+      };
+      auto commit = [](uint32_t bar) { if (CG == 2) umma_commit_cg2_both(bar); else umma_commit(bar); };
+      // descriptors: only the 14-bit start-address field changes (stage, K = 16 slice), added to a prebuilt base
+      const uint64_t adesc0 = smem_desc_sw128(a_base), bdesc0 = smem_desc_sw128(b_base), a2desc0 = smem_desc_sw128(a2_base);
+      const uint32_t a_step = kABytes >> 4, b_step = static_cast<uint32_t>(b_bytes) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;        // tiles issued by this CTA
       int halves = 0;    // mixing halves issued
       auto mix_mma = [&](int h) {
-        if (h == 0) mbar_wait(bar_a2, (it - 1) & 1);                 // A operand of tile it-1 written (pass 1)
-        mbar_wait(bar_nempty, (halves & 1) ^ 1u);                    // previous half drained by the epilogue
+        if (h == 0) SGA_TIMED(2, wait_x(bar_a2, (it - 1) & 1));      // A operand of tile it-1 written (pass 1)
+        SGA_TIMED(3, wait_x(bar_nempty, (halves & 1) ^ 1u));         // previous half drained by the epilogue
         tcgen05_fence_after();
         for (int kc = 0; kc < NF / 64; ++kc) {
           mbar_wait(bar_full + 8 * stage, phase);
           tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = a2desc0 + static_cast<uint64_t>(kc * (kABytes >> 4));
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * b_step);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_base + kNormCol, smem_desc_sw128(a2_base + kc * kABytes + kk * 32),
-                      smem_desc_sw128(b_base + stage * b_bytes + kk * 32), idesc_mix, (kc | kk) != 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * stage);
+            for (int kk = 0; kk < 4; ++kk) mma(tmem_base + kNormCol, ad + 2 * kk, bd + 2 * kk, idesc_mix, (kc | kk) != 0 ? 1u : 0u);
+            commit(bar_empty + 8 * stage);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_nfull);
+        if (elect_one()) commit(bar_nfull);
         ++halves;
       };
       for (int w = 0; w < nwaves; ++w) {
         TileCoord tc_;
-        if (!decode_slot(P, w, tc_)) continue;
+        if (!decode_slot<CG>(P, w, rank, tc_)) continue;
         const int nk = P.job[tc_.job].ntaps * P.kchunks;
         const int ins0 = (P.mix_at0 * nk) / 8, ins1 = (P.mix_at1 * nk) / 8 < nk ? (P.mix_at1 * nk) / 8 : nk - 1;
         const int buf = it & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+        SGA_TIMED(1, wait_x(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u));
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int k = 0; k < nk; ++k) {
@@ -305,20 +385,28 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
             if (k == ins0) mix_mma(0);
             if (k == ins1) mix_mma(1);
           }
-          mbar_wait(bar_full + 8 * stage, phase);
+          SGA_TIMED(0, mbar_wait(bar_full + 8 * stage, phase));
           tcgen05_fence_after();
-          const uint32_t a_addr = a_base + stage * kABytes, b_addr = b_base + stage * b_bytes;
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * a_step);
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * b_step);
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk)
-            umma_bf16(d_tmem, smem_desc_sw128(a_addr + kk * 32), smem_desc_sw128(b_addr + kk * 32), idesc,
-                      (k | kk) != 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs have read it
+            for (int kk = 0; kk < kBlockK / 16; ++kk) mma(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            commit(bar_empty + 8 * stage);        // frees the smem stage (in both CTAs) once these MMAs have read it
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_tfull + 8 * buf);       // accumulator complete
+        if (elect_one()) commit(bar_tfull + 8 * buf);            // accumulator complete
         ++it;
       }
       if (FUSE != 0 && it > 0) { mix_mma(0); mix_mma(1); }
+      if (dbg_t && lane == 0 && (blockIdx.x < 2 || blockIdx.x == 74)) {
+        unsigned long long g1 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        printf("dbg cta %d mma: total %lld (%.0f MHz) wait_full %lld wait_tempty %lld wait_a2 %lld wait_nempty %lld tiles %d\n",
+               blockIdx.x, clock64() - dbg_t0, 1000.0 * static_cast<double>(clock64() - dbg_t0) / static_cast<double>(g1 - dbg_g0),
+               dbg_w[0], dbg_w[1], dbg_w[2], dbg_w[3], it);
+      }
     }
   } else {
     // ===================== epilogue (warps 2 .. 2+4G) =====================
@@ -330,11 +418,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
     int halves = 0;
     for (int w = 0; w < nwaves; ++w) {
       TileCoord tc_;
-      if (!decode_slot(P, w, tc_)) continue;
+      if (!decode_slot<CG>(P, w, rank, tc_)) continue;
       const TcJob& J = P.job[tc_.job];
       const int buf = it & 1;
       const int i = tc_.h0 + row / P.TW, j = tc_.w0 + row % P.TW;
-      const bool valid = (i < J.Ho) && (j < J.Wo);
+      const bool valid = (i < J.Ho) && (j < J.Wo) && (tc_.img < P.N);
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
       // fused backward: the saved x / s of this warp's two chunks are fetched before the accumulator is awaited
       uint32_t xin[(FUSE == 2) ? 2 : 1][16], sin[(FUSE == 2) ? 2 : 1][16];
@@ -353,7 +441,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           }
         }
       }
-      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      SGA_TIMED(0, mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1));
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + lane_off;
       if (FUSE == 0) {
@@ -372,7 +460,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (lane == 0) arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
       } else {
         // ---------- pass 1: accumulator -> (x | g*s) kept in registers as packed bf16, mixing operand -> smem
         uint32_t keep[2][16];
@@ -435,10 +523,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
                 make_uint4(a2w[4 * u], a2w[4 * u + 1], a2w[4 * u + 2], a2w[4 * u + 3]);
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_a2);
+        arrive_lead(bar_a2, lead_a2);
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (lane == 0) arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
         if (use_tma && !(P.dbg & 1)) {
           named_bar_sync(1 + grp, 128);
           if (elected) {
@@ -451,14 +539,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = grp + h * G;
-          mbar_wait(bar_nfull, halves & 1);
+          SGA_TIMED(1, mbar_wait(bar_nfull, halves & 1));
           tcgen05_fence_after();
           uint32_t r[32];
           tmem_ld32(tmem_base + kNormCol + lane_off + grp * 32, r);
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_nempty);       // the mixing result is in registers: release the TMEM region
+          if (lane == 0) arrive_lead(bar_nempty, lead_nempty);   // the mixing result is in registers: release the TMEM region
           ++halves;
           uint32_t o[16], so[16];
 #pragma unroll
@@ -511,13 +599,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       ++it;
     }
     if (FUSE == 1 && P.tma_store) bulk_wait_all();   // (only the electing threads have groups outstanding)
+    if (dbg_t && threadIdx.x == 64 && (blockIdx.x < 2 || blockIdx.x == 74))
+      printf("dbg cta %d epilogue: total %lld wait_tfull %lld wait_nfull %lld tiles %d\n", blockIdx.x, clock64() - dbg_t0,
+             dbg_w[0], dbg_w[1], it);
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's shared memory / barriers are in use until here
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -567,6 +658,7 @@ struct TcConv {
   int smem_bytes;
   int grid;
   int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
+  int cg;     // 1, or 2 = CTA pairs (cluster of two, tcgen05.mma.cta_group::2)
   const void* omap_ptr[3];   // tensors the forward-fusion store maps were encoded for
   ConvPlan plan;
 };
@@ -578,12 +670,37 @@ static int pick_block_n(int Nn) {
 }
 
 typedef void (*TcKernel)(const TcParams);
-static TcKernel select_kernel(int fuse, int nf) {
-  if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups>;
-  if (fuse == 1) return nf == 192 ? k_conv_tc<1, 192, 3> : (nf == 128 ? k_conv_tc<1, 128, 2> : k_conv_tc<1, 64, 1>);
-  return nf == 192 ? k_conv_tc<2, 192, 3> : (nf == 128 ? k_conv_tc<2, 128, 2> : k_conv_tc<2, 64, 1>);
+template <int CG>
+static TcKernel select_kernel_cg(int fuse, int nf) {
+  if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups, CG>;
+  if (fuse == 1)
+    return nf == 192 ? k_conv_tc<1, 192, 3, CG> : (nf == 128 ? k_conv_tc<1, 128, 2, CG> : k_conv_tc<1, 64, 1, CG>);
+  return nf == 192 ? k_conv_tc<2, 192, 3, CG> : (nf == 128 ? k_conv_tc<2, 128, 2, CG> : k_conv_tc<2, 64, 1, CG>);
+}
+static TcKernel select_kernel(int fuse, int nf, int cg) {
+  return cg == 2 ? select_kernel_cg<2>(fuse, nf) : select_kernel_cg<1>(fuse, nf);
 }
 static int kernel_threads(int fuse, int nf) { return 64 + 128 * (fuse == 0 ? kPlainGroups : nf / 64); }
+
+// one launch path for both modes: CTA pairs need the cluster dimension attribute
+static int launch_tc(const TcConv* c, const TcParams& P, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(c->grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(kernel_threads(c->fuse, P.Nn)), 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(c->smem_bytes);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(c->cg);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SGA_CUDA(cudaLaunchKernelEx(&cfg, select_kernel(c->fuse, P.Nn, c->cg), P));
+  g_launches += 1;
+  return SGA_OK;
+}
 
 bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192; }
 
@@ -598,6 +715,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   TcConv* c = new TcConv();
   memset(&c->P, 0, sizeof(c->P));
   c->fuse = fuse;
+  c->cg = (getenv("SGA_NO_PAIR") == nullptr) ? 2 : 1;
   c->plan = plan;
   c->omap_ptr[0] = c->omap_ptr[1] = c->omap_ptr[2] = nullptr;
   TcParams& P = c->P;
@@ -620,8 +738,10 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.TH = kBlockM / P.TW;
   P.tiles_h = ceil_div(plan.job[0].Ho, P.TH);
   P.tiles_w = ceil_div(plan.job[0].Wo, P.TW);
-  P.n_spatial = g.N * P.tiles_h * P.tiles_w * P.n_tiles_n;
-  const int b_bytes = P.block_n * kBlockK * 2;
+  P.n_sp = g.N * P.tiles_h * P.tiles_w;
+  P.n_sp_pairs = (P.n_sp + 1) / 2;
+  P.n_spatial = P.n_sp * P.n_tiles_n;
+  const int b_bytes = (P.block_n / c->cg) * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
   const int stg_bytes = (fuse == 1) ? (g.Cout / 64) * 16384 : 0;
   const int fixed = 1024 + a2_bytes + stg_bytes + 512 * 4 + 256;
@@ -662,7 +782,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     const int taps = g.kh * g.kw;
     const uint64_t dims[2] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(taps) * g.Cout};
     const uint64_t strides[1] = {static_cast<uint64_t>(g.Cin) * 2};
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(P.block_n)};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(P.block_n / c->cg)};
     int st = tma_encode_tiled(&P.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_kmajor, dims, strides, box,
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
@@ -670,7 +790,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   if (fuse) {
     const uint64_t dims[2] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(g.Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(g.Cout) * 2};
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(g.Cout / 2)};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(g.Cout / 2 / c->cg)};
     int st = tma_encode_tiled(&P.gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, mix_op, dims, strides, box,
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
@@ -678,8 +798,13 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c->grid = (P.n_spatial < sms) ? P.n_spatial : sms;
-  SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (c->cg == 2) {
+    const int units = P.n_sp_pairs * P.n_tiles_n, pairs = sms / 2;
+    c->grid = 2 * (units < pairs ? units : pairs);
+  } else {
+    c->grid = (P.n_spatial < sms) ? P.n_spatial : sms;
+  }
+  SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout, c->cg), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return SGA_OK;
 }
@@ -692,9 +817,7 @@ int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bflo
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.bias = bias; P.relu = relu; P.mask = relu_mask; P.out_bf16 = out_bf16; P.out_f32 = out_f32;
-  k_conv_tc<0, 64, kPlainGroups><<<c->grid, kernel_threads(0, 0), c->smem_bytes, st>>>(P);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_tc(c, P, st);
 }
 
 int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
@@ -723,9 +846,7 @@ int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __n
   }
   TcParams P = c->P;
   P.bias = bias; P.beta = beta; P.xpre_out = xpre_out; P.s_out = s_out; P.out_bf16 = act_out;
-  select_kernel(1, P.Nn)<<<c->grid, kernel_threads(1, P.Nn), c->smem_bytes, st>>>(P);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_tc(c, P, st);
 }
 
 int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
@@ -734,9 +855,7 @@ int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.x_in = x_saved; P.s_in = s_saved; P.out_bf16 = gx_out;
-  select_kernel(2, P.Nn)<<<c->grid, kernel_threads(2, P.Nn), c->smem_bytes, st>>>(P);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_tc(c, P, st);
 }
 
 __global__ void k_pack_weights(const float* __restrict__ w, int taps, int Cin, int Cout, int transposed,
