@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, 4 * G * CG);
     }
-    mbar_init(bar_a2, 128 * G * CG);
+    mbar_init(bar_a2, 4 * G * CG);
     mbar_init(bar_nfull, 1);
     mbar_init(bar_nempty, 4 * G * CG);
     fence_barrier_init();
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   const uint32_t tmem_base = *s_tmem;
   const int nwaves = num_waves<CG>(P);
   // wait on a barrier the peer CTA arrives on / arrive on a leader barrier
-  auto wait_x = [](uint32_t bar, uint32_t parity) { if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
+  auto wait_x = [](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
   auto arrive_lead = [](uint32_t local_bar, uint32_t lead_bar) { if (CG == 2) mbar_arrive_cluster(lead_bar); else mbar_arrive(local_bar); };
   // SGA_DBG & 8: per-role wait-cycle accounting, printed by the first and one middle CTA (development aid)
   const bool dbg_t = (P.dbg & 8) != 0;
@@ -523,10 +523,12 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
                 make_uint4(a2w[4 * u], a2w[4 * u + 1], a2w[4 * u + 2], a2w[4 * u + 3]);
         }
         fence_proxy_async_smem();
-        arrive_lead(bar_a2, lead_a2);
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
+        if (lane == 0) {
+          arrive_lead(bar_a2, lead_a2);
+          arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
+        }
         if (use_tma && !(P.dbg & 1)) {
           named_bar_sync(1 + grp, 128);
           if (elected) {

@@ -97,7 +97,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 // arrive on an mbarrier given by its shared::cluster address (own or peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): .release.cluster compiles to
+  // MEMBAR.ALL.CTA + ERRBAR in front of every arrive, which cost the fused epilogues a third of their time
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // ---------------- proxies / fences ----------------
