@@ -270,8 +270,8 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
                               rate_scale, c->b_yt, c->gy_rate, c->dy, c->b_gh2, c->acc, g.first_image * (d.ny / d.N), st));
   for (int i = 0; i < 3; ++i) {
     if (c->fused) {
-      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch_igdn_fwd(c->tc_gs[i], c->gs[i].bias, c->gs_beta[i], c->b_xpre[i],
-                                                                c->b_s[i], c->b_act[i], st));
+      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch_igdn_fwd(c->tc_gs[i], c->gs[i].bias, c->gs_beta[i], c->b_s[i],
+                                                                c->b_act[i], st));
     } else {
       PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
       PROF(c, SGA_PROF_IGDN_FWD, st, igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
@@ -289,8 +289,8 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
       // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
       // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
       PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
-      PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_xpre[1], c->b_s[1], c->b_gb[1], st));
-      PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_xpre[0], c->b_s[0], c->b_gb[0], st));
+      PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
+      PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
       PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
     } else {
       PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
@@ -466,8 +466,9 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
     }
     SGA_TRY(c->alloc(&c->l3_wscatter, 80 * C)); SGA_TRY(c->alloc(&c->l3_wgather, 80 * C));
     SGA_TRY(l3_pack_weights(c->gs[3].w, C, c->l3_wscatter, c->l3_wgather, st));
-    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, c->fused ? c->gs_gamma_b[2] : nullptr, c->b_xpre[2],
-                         c->b_s[2], d.N, d.Hs[3], d.Ws[3], C, d.H, d.W, &c->l3));
+    // fused: the IGDN backward recovers x_2 from the saved act_2 and s_2 (the fused forward does not store x)
+    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, c->fused ? c->gs_gamma_b[2] : nullptr,
+                         c->fused ? c->b_act[2] : c->b_xpre[2], c->b_s[2], d.N, d.Hs[3], d.Ws[3], C, d.H, d.W, &c->l3));
     SGA_CUDA(cudaStreamSynchronize(st));
   }
   c->bound = true;

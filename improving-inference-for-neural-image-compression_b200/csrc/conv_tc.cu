@@ -32,92 +32,12 @@
 #include "kernels.h"
 #include "tc_kernels.h"
 #include "tc_common.cuh"
+#include "conv_tc.cuh"
 #include <stdlib.h>
 
 namespace sga {
 
 using namespace tc;
-
-constexpr int kPlainGroups = 2;                  // epilogue warp groups of the un-fused kernel
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kMaxStages = 8;
-constexpr int kTmemCols = 512;
-
-struct TcJob {
-  int tap_begin, ntaps;
-  int Ho, Wo;             // pixel grid of the output view
-  long long out_off;      // element offset of the output view
-  long long oH, oW;       // element strides of the output view
-};
-
-struct alignas(64) TcParams {
-  CUtensorMap amap[kMaxViews];
-  CUtensorMap bmap;
-  CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
-  CUtensorMap omap[3][4]; // fused IGDN forward: TMA-store maps of x / s / act for each output phase, box {32, TW, TH, 1}
-  int tma_store;          // fused forward: stage the three outputs in shared memory and store them with TMA
-  TcJob job[4];
-  Tap taps[kMaxTaps];
-  int njobs, N, K, Nn;
-  int block_n, n_tiles_n, kchunks, stages;
-  int TH, TW, tiles_h, tiles_w;
-  int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
-  int n_sp;               // spatial tiles per job and N tile = N * tiles_h * tiles_w
-  int n_sp_pairs;         // CTA-pair mode: ceil(n_sp / 2)
-  int relu;
-  int dbg;                // debug/timing experiments only (env SGA_DBG): 1 skip xpre store, 2 skip s store, 4 skip out store
-  int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
-  long long oN;
-  const float* bias;
-  const __nv_bfloat16* mask;
-  __nv_bfloat16* out_bf16;
-  float* out_f32;
-  // fused IGDN
-  const float* beta;            // fwd
-  __nv_bfloat16* xpre_out;      // fwd: x = acc + bias
-  __nv_bfloat16* s_out;         // fwd: sqrt(norm)
-  const __nv_bfloat16* x_in;    // bwd: saved x
-  const __nv_bfloat16* s_in;    // bwd: saved s
-};
-
-struct TileCoord { int job, img, h0, w0, n0; };
-
-// slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G)
-// CG = 2: the unit is a pair of horizontally adjacent spatial tiles sharing the N tile; a pair whose second tile does
-// not exist still runs it with img = N (TMA zero-fills the loads, nothing is stored).
-template <int CG>
-__device__ __forceinline__ bool decode_slot(const TcParams& P, int k, uint32_t rank, TileCoord& tc_) {
-  const int jb = k % P.njobs;
-  int sp, nt;
-  if (CG == 1) {
-    int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-    if (t >= P.n_spatial) return false;
-    nt = t % P.n_tiles_n;
-    sp = t / P.n_tiles_n;
-  } else {
-    const int u = (k / P.njobs) * static_cast<int>(gridDim.x >> 1) + static_cast<int>(blockIdx.x >> 1);
-    if (u >= P.n_sp_pairs * P.n_tiles_n) return false;
-    nt = u / P.n_sp_pairs;
-    sp = (u % P.n_sp_pairs) * 2 + static_cast<int>(rank);
-  }
-  if (sp >= P.n_sp) {
-    tc_ = TileCoord{jb, P.N, 0, 0, nt * P.block_n};
-    return true;
-  }
-  const int tw = sp % P.tiles_w; sp /= P.tiles_w;
-  const int th = sp % P.tiles_h;
-  const int img = sp / P.tiles_h;
-  tc_ = TileCoord{jb, img, th * P.TH, tw * P.TW, nt * P.block_n};
-  return true;
-}
-template <int CG>
-__device__ __forceinline__ int num_waves(const TcParams& P) {
-  const int units = (CG == 1) ? P.n_spatial : P.n_sp_pairs * P.n_tiles_n;
-  const int g = static_cast<int>(gridDim.x) / CG;
-  return ((units + g - 1) / g) * P.njobs;
-}
 
 template <int NV>
 __device__ __forceinline__ void epilogue_store(const TcParams& P, const uint32_t (&r)[NV], const float* s_bias, int ncol,
@@ -161,20 +81,6 @@ __device__ __forceinline__ void epilogue_store(const TcParams& P, const uint32_t
       st_global_v8(P.out_f32 + off + q * 8, w);
     }
   }
-}
-
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float y;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_rcp(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
 }
 
 // FUSE: 0 = plain conv epilogue, 1 = + IGDN forward, 2 = + IGDN backward.  NF = Cout of the fused variants.
@@ -496,11 +402,15 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
                 const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);     // the stored (bf16) x is what the mixing sees
                 a2w[e] = pack_bf16(x0 * x0, x1 * x1);
               } else {
-                const uint32_t xw = xin[(FUSE == 2) ? h : 0][e];
+                // the forward stores act = x*s and s: x = act / s
+                const uint32_t aw = xin[(FUSE == 2) ? h : 0][e];
                 const uint32_t sw = sin[(FUSE == 2) ? h : 0][e];
-                const float x0 = bf16_lo(xw), x1 = bf16_hi(xw), s0 = bf16_lo(sw), s1 = bf16_hi(sw);
+                const float s0 = bf16_lo(sw), s1 = bf16_hi(sw);
+                const float r0 = fast_rcp(s0), r1 = fast_rcp(s1);
+                const float x0 = bf16_lo(aw) * r0, x1 = bf16_hi(aw) * r1;
+                xin[(FUSE == 2) ? h : 0][e] = pack_bf16(x0, x1);
                 keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
-                a2w[e] = pack_bf16(v0 * x0 * fast_rcp(s0), v1 * x1 * fast_rcp(s1));
+                a2w[e] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
               }
             }
           }
@@ -655,15 +565,6 @@ int tma_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const v
   return SGA_OK;
 }
 
-struct TcConv {
-  TcParams P;
-  int smem_bytes;
-  int grid;
-  int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
-  int cg;     // 1, or 2 = CTA pairs (cluster of two, tcgen05.mma.cta_group::2)
-  const void* omap_ptr[3];   // tensors the forward-fusion store maps were encoded for
-  ConvPlan plan;
-};
 
 static int pick_block_n(int Nn) {
   for (int bn = 256; bn >= 16; bn -= 16)
@@ -675,8 +576,6 @@ typedef void (*TcKernel)(const TcParams);
 template <int CG>
 static TcKernel select_kernel_cg(int fuse, int nf) {
   if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups, CG>;
-  if (fuse == 1)
-    return nf == 192 ? k_conv_tc<1, 192, 3, CG> : (nf == 128 ? k_conv_tc<1, 128, 2, CG> : k_conv_tc<1, 64, 1, CG>);
   return nf == 192 ? k_conv_tc<2, 192, 3, CG> : (nf == 128 ? k_conv_tc<2, 128, 2, CG> : k_conv_tc<2, 64, 1, CG>);
 }
 static TcKernel select_kernel(int fuse, int nf, int cg) {
@@ -731,7 +630,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     P.mix_at0 = e0 ? atoi(e0) : 6; P.mix_at1 = e1 ? atoi(e1) : 8;
     const char* ed = getenv("SGA_DBG");
     P.dbg = ed ? atoi(ed) : 0;
-    P.tma_store = (fuse == 1 && getenv("SGA_NO_TMA_STORE") == nullptr) ? 1 : 0;
+    P.tma_store = 0;
   }
   P.oN = static_cast<long long>(g.Hout) * g.Wout * g.Cout;
   // spatial tile: 128 pixels = TH x TW
@@ -746,7 +645,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   const int b_bytes = (P.block_n / c->cg) * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
   const int stg_bytes = (fuse == 1) ? (g.Cout / 64) * 16384 : 0;
-  const int fixed = 1024 + a2_bytes + stg_bytes + 512 * 4 + 256;
+  const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + stg_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* es = getenv("SGA_DBG_STAGES")) { const int v = atoi(es); if (v >= 2 && v < stages) stages = v; }
@@ -792,7 +691,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   if (fuse) {
     const uint64_t dims[2] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(g.Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(g.Cout) * 2};
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(g.Cout / 2 / c->cg)};
+    // backward fusion: halves of the result (N/2 rows per MMA); forward fusion: 64-column parts
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>((fuse == 1 ? 64 : g.Cout / 2) / c->cg)};
     int st = tma_encode_tiled(&P.gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, mix_op, dims, strides, box,
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
@@ -806,7 +706,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   } else {
     c->grid = (P.n_spatial < sms) ? P.n_spatial : sms;
   }
-  SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout, c->cg), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (fuse == 1) SGA_TRY(igdn_fwd_set_attr(g.Cout, c->cg));
+  else SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout, c->cg), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return SGA_OK;
 }
@@ -822,41 +723,21 @@ int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bflo
   return launch_tc(c, P, st);
 }
 
-int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
-                            __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st) {
+int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* s_out, __nv_bfloat16* act_out,
+                            cudaStream_t st) {
   SGA_CHECK(c->fuse == 1, "conv was not created with forward IGDN fusion");
   if (c->P.n_spatial == 0) return SGA_OK;
-  if (c->P.tma_store) {
-    // (re)encode the store maps when the output tensors change: one 4-D view {C, Wo, Ho, N} per tensor and output phase
-    const void* ptrs[3] = {xpre_out, s_out, act_out};
-    const ConvGeom& g = c->plan.g;
-    for (int t = 0; t < 3; ++t) {
-      if (c->omap_ptr[t] == ptrs[t]) continue;
-      for (int jn = 0; jn < c->P.njobs; ++jn) {
-        const TcJob& J = c->P.job[jn];
-        const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(J.Wo), static_cast<uint64_t>(J.Ho),
-                                  static_cast<uint64_t>(g.N)};
-        const uint64_t strides[3] = {static_cast<uint64_t>(J.oW) * 2, static_cast<uint64_t>(J.oH) * 2,
-                                     static_cast<uint64_t>(c->P.oN) * 2};
-        const uint32_t box[4] = {32, static_cast<uint32_t>(c->P.TW), static_cast<uint32_t>(c->P.TH), 1};
-        SGA_TRY(tma_encode_tiled(&c->P.omap[t][jn], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                                 static_cast<const __nv_bfloat16*>(ptrs[t]) + J.out_off, dims, strides, box,
-                                 CU_TENSOR_MAP_SWIZZLE_64B));
-      }
-      c->omap_ptr[t] = ptrs[t];
-    }
-  }
   TcParams P = c->P;
-  P.bias = bias; P.beta = beta; P.xpre_out = xpre_out; P.s_out = s_out; P.out_bf16 = act_out;
-  return launch_tc(c, P, st);
+  P.bias = bias; P.beta = beta; P.s_out = s_out; P.out_bf16 = act_out;
+  return launch_igdn_fwd_kernel(c, P, st);
 }
 
-int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
+int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* act_saved, const __nv_bfloat16* s_saved,
                             __nv_bfloat16* gx_out, cudaStream_t st) {
   SGA_CHECK(c->fuse == 2, "conv was not created with backward IGDN fusion");
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
-  P.x_in = x_saved; P.s_in = s_saved; P.out_bf16 = gx_out;
+  P.x_in = act_saved; P.s_in = s_saved; P.out_bf16 = gx_out;
   return launch_tc(c, P, st);
 }
 

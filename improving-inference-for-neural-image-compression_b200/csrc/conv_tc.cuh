@@ -1,0 +1,120 @@
+// conv_tc.cuh -- definitions shared by the tcgen05 (de)conv kernels (conv_tc.cu, conv_igdn_fwd_tc.cu)
+#pragma once
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace sga {
+
+using namespace tc;
+
+constexpr int kPlainGroups = 2;                  // epilogue warp groups of the un-fused kernel
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+
+struct TcJob {
+  int tap_begin, ntaps;
+  int Ho, Wo;             // pixel grid of the output view
+  long long out_off;      // element offset of the output view
+  long long oH, oW;       // element strides of the output view
+};
+
+struct alignas(64) TcParams {
+  CUtensorMap amap[kMaxViews];
+  CUtensorMap bmap;
+  CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
+  CUtensorMap omap[3][4]; // fused IGDN forward: TMA-store maps of x / s / act for each output phase, box {32, TW, TH, 1}
+  int tma_store;          // fused forward: stage the three outputs in shared memory and store them with TMA
+  TcJob job[4];
+  Tap taps[kMaxTaps];
+  int njobs, N, K, Nn;
+  int block_n, n_tiles_n, kchunks, stages;
+  int TH, TW, tiles_h, tiles_w;
+  int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
+  int n_sp;               // spatial tiles per job and N tile = N * tiles_h * tiles_w
+  int n_sp_pairs;         // CTA-pair mode: ceil(n_sp / 2)
+  int relu;
+  int dbg;                // debug/timing experiments only (env SGA_DBG): 1 skip xpre store, 2 skip s store, 4 skip out store
+  int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
+  long long oN;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  // fused IGDN
+  const float* beta;            // fwd
+  __nv_bfloat16* xpre_out;      // fwd: x = acc + bias
+  __nv_bfloat16* s_out;         // fwd: sqrt(norm)
+  const __nv_bfloat16* x_in;    // bwd: saved act = x*s
+  const __nv_bfloat16* s_in;    // bwd: saved s
+};
+
+struct TileCoord { int job, img, h0, w0, n0; };
+
+// slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G)
+// CG = 2: the unit is a pair of horizontally adjacent spatial tiles sharing the N tile; a pair whose second tile does
+// not exist still runs it with img = N (TMA zero-fills the loads, nothing is stored).
+template <int CG>
+__device__ __forceinline__ bool decode_slot(const TcParams& P, int k, uint32_t rank, TileCoord& tc_) {
+  const int jb = k % P.njobs;
+  int sp, nt;
+  if (CG == 1) {
+    int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+    if (t >= P.n_spatial) return false;
+    nt = t % P.n_tiles_n;
+    sp = t / P.n_tiles_n;
+  } else {
+    const int u = (k / P.njobs) * static_cast<int>(gridDim.x >> 1) + static_cast<int>(blockIdx.x >> 1);
+    if (u >= P.n_sp_pairs * P.n_tiles_n) return false;
+    nt = u / P.n_sp_pairs;
+    sp = (u % P.n_sp_pairs) * 2 + static_cast<int>(rank);
+  }
+  if (sp >= P.n_sp) {
+    tc_ = TileCoord{jb, P.N, 0, 0, nt * P.block_n};
+    return true;
+  }
+  const int tw = sp % P.tiles_w; sp /= P.tiles_w;
+  const int th = sp % P.tiles_h;
+  const int img = sp / P.tiles_h;
+  tc_ = TileCoord{jb, img, th * P.TH, tw * P.TW, nt * P.block_n};
+  return true;
+}
+template <int CG>
+__device__ __forceinline__ int num_waves(const TcParams& P) {
+  const int units = (CG == 1) ? P.n_spatial : P.n_sp_pairs * P.n_tiles_n;
+  const int g = static_cast<int>(gridDim.x) / CG;
+  return ((units + g - 1) / g) * P.njobs;
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct TcConv {
+  TcParams P;
+  int smem_bytes;
+  int grid;
+  int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
+  int cg;     // 1, or 2 = CTA pairs (cluster of two, tcgen05.mma.cta_group::2)
+  const void* omap_ptr[3];   // tensors the forward-fusion store maps were encoded for
+  ConvPlan plan;
+};
+
+// conv_igdn_fwd_tc.cu: the forward (de)conv fused with the inverse GDN (fuse == 1)
+int igdn_fwd_smem_fixed(int cout, int cg);          // shared memory outside the operand ring
+int igdn_fwd_set_attr(int cout, int cg);
+int launch_igdn_fwd_kernel(const TcConv* c, const TcParams& P, cudaStream_t st);
+
+}  // namespace sga

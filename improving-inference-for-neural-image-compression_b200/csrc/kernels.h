@@ -79,11 +79,11 @@ void tc_conv_destroy(TcConv* c);
 // epilogue: v = acc + bias[n]; relu; *= (mask > 0); store as bf16 (out_bf16) and/or fp32 (out_f32)
 int tc_conv_launch(const TcConv* c, const float* bias, int relu, const __nv_bfloat16* relu_mask, __nv_bfloat16* out_bf16,
                    float* out_f32, cudaStream_t st);
-// x = acc + bias; s = sqrt(beta + x^2 @ gamma); act = x*s  -- all three stored as bf16
-int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* xpre_out,
-                            __nv_bfloat16* s_out, __nv_bfloat16* act_out, cudaStream_t st);
-// g = acc; g_x = g*s + x*((g*x/s) @ gamma^T) stored as bf16
-int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* x_saved, const __nv_bfloat16* s_saved,
+// x = acc + bias; s = sqrt(beta + x^2 @ gamma); act = x*s  -- s and act stored as bf16 (x = act / s in the backward)
+int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __nv_bfloat16* s_out, __nv_bfloat16* act_out,
+                            cudaStream_t st);
+// g = acc; x = act/s; g_x = g*s + x*((g*x/s) @ gamma^T) stored as bf16
+int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* act_saved, const __nv_bfloat16* s_saved,
                             __nv_bfloat16* gx_out, cudaStream_t st);
 // w_ref (kh,kw,Cin,Cout) fp32 -> K-major bf16 B operand: [tap][Nn][K] (K = Cin for forward kinds, Cout for dgrads)
 int launch_pack_weights_bf16(const float* w_ref, int taps, int Cin, int Cout, bool transposed, __nv_bfloat16* out,

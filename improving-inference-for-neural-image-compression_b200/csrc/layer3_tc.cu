@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kL3dThreads, 1) k_l3_dgrad(const __grid_consta
 // =====================================================================================================
 struct alignas(64) L3DgradFusedParams {
   CUtensorMap gmap;            // gamma [n = C rows][k = C cols] bf16, box {64, C}
-  CUtensorMap xmap, smap;      // saved x_2 / s_2 [N,Hin,Win,C] bf16, box {64, 16, 8, 1}
+  CUtensorMap xmap, smap;      // saved act_2 (= x_2*s_2) / s_2 [N,Hin,Win,C] bf16, box {64, 16, 8, 1}
   const __nv_bfloat16* gx;     // [N,Ho,Wo,4]
   const __nv_bfloat16* wpack;  // [10][C][8]
   __nv_bfloat16* out;          // d loss / d x_2
@@ -670,11 +670,14 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
           for (int e4 = 0; e4 < 4; ++e4) {
             const int e = u * 4 + e4;
             const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-            const uint32_t xw = xk[h][e];
+            const uint32_t aw = xk[h][e];                        // saved act = x*s: x = act / s
             const uint32_t sw = valid ? sv[e] : 0x3F803F80u;     // out-of-image rows are zero-filled by TMA: s = 1
-            const float x0 = l3_bf16_lo(xw), x1 = l3_bf16_hi(xw), s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
+            const float s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
+            const float r0 = l3_rcp(s0), r1 = l3_rcp(s1);
+            const float x0 = l3_bf16_lo(aw) * r0, x1 = l3_bf16_hi(aw) * r1;
+            xk[h][e] = pack_bf16(x0, x1);
             keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
-            a2w[e4] = pack_bf16(v0 * x0 * l3_rcp(s0), v1 * x1 * l3_rcp(s1));
+            a2w[e4] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
           }
           *reinterpret_cast<uint4*>(xc + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
         }
