@@ -53,6 +53,18 @@ def flops_per_iteration(n, h, w, c):
     return f, 2.0 * fwd
 
 
+def measured_traffic():
+    """DRAM bytes of the (de)conv launches of one step from the newest committed `ncu --set full` capture
+    (profiles/*_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as fh:
+        d = json.load(fh)
+    return d.get("conv_dram_bytes_per_launch"), os.path.basename(files[-1])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,6 +296,9 @@ def main_ours(args, rank, ws, local):
     conv_fl = sum(fl[conv_labels[k]] * prof[k][1] for k in conv_labels if k in prof)
     conv_launches = sum(prof[k][1] for k in conv_labels if k in prof)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, traffic_src = measured_traffic()
+    if traffic is not None and ws > 1:
+        traffic = traffic / ws          # the capture is of the 24-image job on one GPU
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
     per_layer = {k: round(fl[conv_labels[k]] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12, 1) for k in conv_labels
                  if k in prof and prof[k][0] > 0}
@@ -298,9 +313,11 @@ def main_ours(args, rank, ws, local):
         "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 * ws),
                 "d2h_bytes_per_step": int(eng.n_stats * 4 * ws), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM (de)conv, all 12 launches/step)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "tcgen05 implicit-GEMM (de)conv kernels: k_conv_tc x9 + k_conv_igdn_fwd x3 per step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "traffic": None, "peak_source": pk["source"], "launches_timed": conv_launches,
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean over the 12 launches, 24 images)",
+                     "traffic_source": traffic_src, "peak_source": pk["source"], "launches_timed": conv_launches,
                      "per_layer_tflops": per_layer,
                      "whole_step_tflops": flops_iter * value / 1e12,
                      "whole_step_frac": flops_iter * value / 1e12 / pk["tflops"]},
