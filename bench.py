@@ -292,15 +292,20 @@ def main_ours(args, rank, ws, local):
     conv_labels = {"hs0_fwd": "hs0", "hs1_fwd": "hs1", "hs2_fwd": "hs2", "hs0_dgrad": "hs0", "hs1_dgrad": "hs1",
                    "hs2_dgrad": "hs2", "gs0_fwd": "gs0", "gs1_fwd": "gs1", "gs2_fwd": "gs2", "gs0_dgrad": "gs0",
                    "gs1_dgrad": "gs1", "gs2_dgrad": "gs2"}
+    # algorithmic FLOPs executed inside each (de)conv launch: the conv itself plus the IGDN channel mixing fused into it
+    # (forward: IGDN_i after conv_i; backward: IGDN_{i-1} in the dgrad of conv_i; IGDN_2's backward is in k_l3_dgrad_igdn)
+    fused_extra = {"gs0_fwd": "igdn0", "gs1_fwd": "igdn1", "gs2_fwd": "igdn2", "gs1_dgrad": "igdn0", "gs2_dgrad": "igdn1"}
+    kfl = {k: fl[conv_labels[k]] + (fl[fused_extra[k]] if (k in fused_extra and C in (64, 128, 192)) else 0.0)
+           for k in conv_labels}
     conv_ms = sum(prof[k][0] for k in conv_labels if k in prof)
-    conv_fl = sum(fl[conv_labels[k]] * prof[k][1] for k in conv_labels if k in prof)
+    conv_fl = sum(kfl[k] * prof[k][1] for k in conv_labels if k in prof)
     conv_launches = sum(prof[k][1] for k in conv_labels if k in prof)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = measured_traffic()
     if traffic is not None and ws > 1:
         traffic = traffic / ws          # the capture is of the 24-image job on one GPU
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
-    per_layer = {k: round(fl[conv_labels[k]] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12, 1) for k in conv_labels
+    per_layer = {k: round(kfl[k] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12, 1) for k in conv_labels
                  if k in prof and prof[k][0] > 0}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,

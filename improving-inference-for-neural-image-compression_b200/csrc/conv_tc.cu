@@ -92,6 +92,7 @@ template <int FUSE, int NF, int G, int CG>
 __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_constant__ TcParams P) {
   static_assert(FUSE == 0 || G * 64 == NF, "fused variants: one 32-column chunk per warp and half");
   static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
+  static_assert(FUSE == 0 || FUSE == 2, "the forward fusion lives in conv_igdn_fwd_tc.cu");
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
   extern __shared__ uint8_t smem_raw[];
@@ -104,9 +105,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   constexpr int kA2Bytes = (FUSE != 0) ? (NF / 64) * kABytes : 0;
   const uint32_t a2_base = b_base + P.stages * b_bytes;            // fused: A operand of the mixing GEMM
   uint8_t* a2_ptr = smem + P.stages * (kABytes + b_bytes);
-  constexpr int kStgBytes = (FUSE == 1) ? G * 16384 : 0;         // fused fwd: 2 x 8 KB output staging slots per group
-  uint8_t* stg_ptr = a2_ptr + kA2Bytes;
-  uint8_t* tail = stg_ptr + kStgBytes;
+  uint8_t* tail = a2_ptr + kA2Bytes;
   float* s_bias = reinterpret_cast<float*>(tail);                  // 512 floats: bias (or beta for the fused fwd: +256)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512 * sizeof(float));
   // bars: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | a2_full | norm_full | norm_empty
@@ -131,7 +130,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
 
   for (int i = threadIdx.x; i < P.Nn && i < 256; i += blockDim.x) {
     s_bias[i] = P.bias ? P.bias[i] : 0.0f;
-    if (FUSE == 1) s_bias[256 + i] = P.beta[i];
   }
   if (FUSE == 0)
     for (int i = 256 + threadIdx.x; i < P.Nn && i < 512; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
@@ -140,9 +138,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
     for (int v = 0; v < kMaxViews; ++v) tma_prefetch_desc(&P.amap[v]);
     tma_prefetch_desc(&P.bmap);
     if (FUSE != 0) tma_prefetch_desc(&P.gmap);
-    if (FUSE == 1 && P.tma_store)
-      for (int t = 0; t < 3; ++t)
-        for (int jn = 0; jn < P.njobs; ++jn) tma_prefetch_desc(&P.omap[t][jn]);
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -331,7 +326,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       const bool valid = (i < J.Ho) && (j < J.Wo) && (tc_.img < P.N);
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
       // fused backward: the saved x / s of this warp's two chunks are fetched before the accumulator is awaited
-      uint32_t xin[(FUSE == 2) ? 2 : 1][16], sin[(FUSE == 2) ? 2 : 1][16];
+      uint32_t xin[2][16], sin[2][16];
       if (FUSE == 2) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -368,16 +363,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
         __syncwarp();
         if (lane == 0) arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
       } else {
-        // ---------- pass 1: accumulator -> (x | g*s) kept in registers as packed bf16, mixing operand -> smem
+        // ---------- pass 1: accumulator g, saved act / s -> g*s kept in registers as packed bf16, mixing operand -> smem
         uint32_t keep[2][16];
-        const bool use_tma = (FUSE == 1) && P.tma_store;
-        const bool elected = (((warp - 2) & 3) == 0) && lane == 0;     // issues this group's TMA stores
-        uint8_t* stg = stg_ptr + grp * 16384;
-        const uint32_t stg_u32 = smem_u32(stg);
-        if (use_tma) {                       // the previous stores of this group have finished reading the staging slots
-          if (elected) bulk_wait_read0();
-          named_bar_sync(1 + grp, 128);
-        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = grp + h * G;               // 32-column chunk of the tile owned by this warp in half h
@@ -386,44 +373,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           tmem_ld_wait();
           uint32_t a2w[16];
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FUSE == 1) b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * e4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-              const int e = e4 * 2 + e2;
-              float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-              if (FUSE == 1) {
-                v0 += bb[2 * e2];
-                v1 += bb[2 * e2 + 1];
-                const uint32_t xb = pack_bf16(v0, v1);
-                keep[h][e] = xb;
-                const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);     // the stored (bf16) x is what the mixing sees
-                a2w[e] = pack_bf16(x0 * x0, x1 * x1);
-              } else {
-                // the forward stores act = x*s and s: x = act / s
-                const uint32_t aw = xin[(FUSE == 2) ? h : 0][e];
-                const uint32_t sw = sin[(FUSE == 2) ? h : 0][e];
-                const float s0 = bf16_lo(sw), s1 = bf16_hi(sw);
-                const float r0 = fast_rcp(s0), r1 = fast_rcp(s1);
-                const float x0 = bf16_lo(aw) * r0, x1 = bf16_hi(aw) * r1;
-                xin[(FUSE == 2) ? h : 0][e] = pack_bf16(x0, x1);
-                keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
-                a2w[e] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
-              }
-            }
-          }
-          if (FUSE == 1 && !(P.dbg & 1)) {
-            if (use_tma) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                *reinterpret_cast<uint4*>(stg + h * 8192 + sw64_offset(row, u)) =
-                    make_uint4(keep[h][4 * u], keep[h][4 * u + 1], keep[h][4 * u + 2], keep[h][4 * u + 3]);
-            } else if (valid) {
-              st_global_v8(P.xpre_out + off0 + c * 32, &keep[h][0]);
-              st_global_v8(P.xpre_out + off0 + c * 32 + 16, &keep[h][8]);
-            }
+          for (int e = 0; e < 16; ++e) {
+            const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            // the forward stores act = x*s and s: x = act / s
+            const uint32_t aw = xin[h][e];
+            const uint32_t sw = sin[h][e];
+            const float s0 = bf16_lo(sw), s1 = bf16_hi(sw);
+            const float r0 = fast_rcp(s0), r1 = fast_rcp(s1);
+            const float x0 = bf16_lo(aw) * r0, x1 = bf16_hi(aw) * r1;
+            xin[h][e] = pack_bf16(x0, x1);
+            keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
+            a2w[e] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
           }
           // 32 columns = 4 x 16-byte chunks of K-chunk (c/2), chunk index ((c&1)*4 + u) within the 128-byte row
           uint8_t* a2c = a2_ptr + (c >> 1) * kABytes;
@@ -439,14 +399,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           arrive_lead(bar_a2, lead_a2);
           arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
         }
-        if (use_tma && !(P.dbg & 1)) {
-          named_bar_sync(1 + grp, 128);
-          if (elected) {
-            tma_store_4d(&P.omap[0][tc_.job], stg_u32, tc_.n0 + grp * 32, tc_.w0, tc_.h0, tc_.img);
-            tma_store_4d(&P.omap[0][tc_.job], stg_u32 + 8192, tc_.n0 + (grp + G) * 32, tc_.w0, tc_.h0, tc_.img);
-            bulk_commit_group();
-          }
-        }
         // ---------- pass 2: two halves of the mixing result; this warp owns chunk `grp` of each half
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -460,57 +412,22 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           __syncwarp();
           if (lane == 0) arrive_lead(bar_nempty, lead_nempty);   // the mixing result is in registers: release the TMEM region
           ++halves;
-          uint32_t o[16], so[16];
+          uint32_t o[16];
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FUSE == 1) b4 = *reinterpret_cast<const float4*>(s_bias + 256 + c * 32 + 4 * e4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-              const int e = e4 * 2 + e2;
-              const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
-              const uint32_t kw = keep[h][e];
-              if (FUSE == 1) {
-                const float s0 = fast_sqrt(m0 + bb[2 * e2]), s1 = fast_sqrt(m1 + bb[2 * e2 + 1]);
-                o[e] = pack_bf16(bf16_lo(kw) * s0, bf16_hi(kw) * s1);
-                so[e] = pack_bf16(s0, s1);
-              } else {
-                const uint32_t xw = xin[(FUSE == 2) ? h : 0][e];
-                o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
-              }
-            }
+          for (int e = 0; e < 16; ++e) {
+            const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
+            const uint32_t kw = keep[h][e];
+            const uint32_t xw = xin[h][e];
+            o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
           }
-          if (use_tma) {
-            if (elected) bulk_wait_read0();
-            named_bar_sync(1 + grp, 128);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              *reinterpret_cast<uint4*>(stg + sw64_offset(row, u)) = make_uint4(so[4 * u], so[4 * u + 1], so[4 * u + 2], so[4 * u + 3]);
-              *reinterpret_cast<uint4*>(stg + 8192 + sw64_offset(row, u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1 + grp, 128);
-            if (elected) {
-              if (!(P.dbg & 2)) tma_store_4d(&P.omap[1][tc_.job], stg_u32, tc_.n0 + c * 32, tc_.w0, tc_.h0, tc_.img);
-              if (!(P.dbg & 4)) tma_store_4d(&P.omap[2][tc_.job], stg_u32 + 8192, tc_.n0 + c * 32, tc_.w0, tc_.h0, tc_.img);
-              bulk_commit_group();
-            }
-          } else if (valid) {
-            if (!(P.dbg & 4)) {
-              st_global_v8(P.out_bf16 + off0 + c * 32, &o[0]);
-              st_global_v8(P.out_bf16 + off0 + c * 32 + 16, &o[8]);
-            }
-            if (FUSE == 1 && !(P.dbg & 2)) {
-              st_global_v8(P.s_out + off0 + c * 32, &so[0]);
-              st_global_v8(P.s_out + off0 + c * 32 + 16, &so[8]);
-            }
+          if (valid) {
+            st_global_v8(P.out_bf16 + off0 + c * 32, &o[0]);
+            st_global_v8(P.out_bf16 + off0 + c * 32 + 16, &o[8]);
           }
         }
       }
       ++it;
     }
-    if (FUSE == 1 && P.tma_store) bulk_wait_all();   // (only the electing threads have groups outstanding)
     if (dbg_t && threadIdx.x == 64 && (blockIdx.x < 2 || blockIdx.x == 74))
       printf("dbg cta %d epilogue: total %lld wait_tfull %lld wait_nfull %lld tiles %d\n", blockIdx.x, clock64() - dbg_t0,
              dbg_w[0], dbg_w[1], it);
@@ -618,7 +535,6 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   c->fuse = fuse;
   c->cg = (getenv("SGA_NO_PAIR") == nullptr) ? 2 : 1;
   c->plan = plan;
-  c->omap_ptr[0] = c->omap_ptr[1] = c->omap_ptr[2] = nullptr;
   TcParams& P = c->P;
   P.N = g.N; P.K = g.Cin; P.Nn = g.Cout;
   P.block_n = pick_block_n(g.Cout);
@@ -630,7 +546,6 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     P.mix_at0 = e0 ? atoi(e0) : 6; P.mix_at1 = e1 ? atoi(e1) : 8;
     const char* ed = getenv("SGA_DBG");
     P.dbg = ed ? atoi(ed) : 0;
-    P.tma_store = 0;
   }
   P.oN = static_cast<long long>(g.Hout) * g.Wout * g.Cout;
   // spatial tile: 128 pixels = TH x TW
@@ -644,8 +559,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.n_spatial = P.n_sp * P.n_tiles_n;
   const int b_bytes = (P.block_n / c->cg) * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
-  const int stg_bytes = (fuse == 1) ? (g.Cout / 64) * 16384 : 0;
-  const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + stg_bytes + 512 * 4 + 256;
+  const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* es = getenv("SGA_DBG_STAGES")) { const int v = atoi(es); if (v >= 2 && v < stages) stages = v; }

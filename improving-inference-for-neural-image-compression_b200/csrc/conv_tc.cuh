@@ -25,8 +25,6 @@ struct alignas(64) TcParams {
   CUtensorMap amap[kMaxViews];
   CUtensorMap bmap;
   CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
-  CUtensorMap omap[3][4]; // fused IGDN forward: TMA-store maps of x / s / act for each output phase, box {32, TW, TH, 1}
-  int tma_store;          // fused forward: stage the three outputs in shared memory and store them with TMA
   TcJob job[4];
   Tap taps[kMaxTaps];
   int njobs, N, K, Nn;
@@ -45,7 +43,6 @@ struct alignas(64) TcParams {
   float* out_f32;
   // fused IGDN
   const float* beta;            // fwd
-  __nv_bfloat16* xpre_out;      // fwd: x = acc + bias
   __nv_bfloat16* s_out;         // fwd: sqrt(norm)
   const __nv_bfloat16* x_in;    // bwd: saved act = x*s
   const __nv_bfloat16* s_in;    // bwd: saved s
@@ -108,7 +105,6 @@ struct TcConv {
   int grid;
   int fuse;   // 0, 1 (igdn fwd), 2 (igdn bwd)
   int cg;     // 1, or 2 = CTA pairs (cluster of two, tcgen05.mma.cta_group::2)
-  const void* omap_ptr[3];   // tensors the forward-fusion store maps were encoded for
   ConvPlan plan;
 };
 
