@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace sga {
 
@@ -35,6 +36,32 @@ __device__ __forceinline__ float soft_round_one(float v, float u0, float u1, flo
   const float dl1 = p1 / ((1.0f - ec * ec) * T);
   *dvt = (c - f) * s1 * s0 * (dl1 - dl0) / T;
   return f * s0 + c * s1;
+}
+
+// Same function for the bf16 loop (operands are rounded to 8 mantissa bits right after): the two atanh and the two
+// Gumbel terms collapse into two logarithms of ratios,
+//   l1 - l0 = (atanh(d) - atanh(e)) / T = log((1+d)(1-e) / ((1-d)(1+e))) / (2T),   g1 - g0 = log(log(u0) / log(u1)),
+// evaluated with the SFU intrinsics (MUFU.LG2 / EX2 / RCP) where their absolute error is harmless.
+__device__ __forceinline__ float soft_round_fast(float v, float u0, float u1, float T, float eps, float* dvt) {
+  const float f = floorf(v), c = ceilf(v);
+  const float hi = 1.0f - eps;
+  const float d = v - f, e = c - v;                       // both in [0, 1]: only the upper clip can bind
+  const float dc = fminf(d, hi), ec = fminf(e, hi);
+  const float invT = __frcp_rn(T);
+  const float ld = __logf(__fdividef((1.0f + dc) * (1.0f - ec), (1.0f - dc) * (1.0f + ec)));
+  // log(u) keeps the accurate logf: u reaches 1 - 2^-25, where the SFU logarithm's absolute error exceeds the value
+  const float lg = __logf(__fdividef(logf(u0), logf(u1)));
+  const float a = (0.5f * invT * ld + lg) * invT;
+  const float s1 = __frcp_rn(1.0f + __expf(-a));
+  const float s0 = 1.0f - s1;
+  const float p0 = (d <= hi) ? 1.0f : 0.0f, p1 = (e <= hi) ? 1.0f : 0.0f;
+  const float dl = p1 * __frcp_rn(1.0f - ec * ec) + p0 * __frcp_rn(1.0f - dc * dc);     // T * (dl1 - dl0)
+  *dvt = (c - f) * s1 * s0 * dl * invT * invT;
+  return f * s0 + c * s1;
+}
+template <bool FAST>
+__device__ __forceinline__ float soft_round_sel(float v, float u0, float u1, float T, float eps, float* dvt) {
+  return FAST ? soft_round_fast(v, u0, u1, T, eps, dvt) : soft_round_one(v, u0, u1, T, eps, dvt);
 }
 
 __device__ __forceinline__ void pair_uniforms(const float* __restrict__ inj, long long numel, long long e0,
@@ -201,7 +228,7 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
       if (e < numel) {
         float d = 0.0f, zt;
         if (hard) zt = rintf(z[e]);
-        else zt = soft_round_one(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
+        else zt = soft_round_sel<std::is_same<AT, __nv_bfloat16>::value>(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
         EbParams P;
         eb_load(pk, C, static_cast<int>(e % C), P);
         float dp;
@@ -248,6 +275,25 @@ __device__ __forceinline__ float gauss_likelihood_one(float yt, float mu, float 
   return p;
 }
 
+// bf16-loop variant: one reciprocal instead of four divisions, SFU exponentials (erfc stays the accurate one: the
+// likelihood reaches 1e-9 in the tails and enters the loss through its logarithm)
+__device__ __forceinline__ float gauss_likelihood_fast(float yt, float mu, float logsigma, float* dp_dy, float* dp_dsb,
+                                                       float* sigma_out) {
+  const float sigma = __expf(logsigma);
+  const float sb = fmaxf(sigma, 0.11f);
+  const float inv = __frcp_rn(sb);
+  const float d = yt - mu;
+  const float v = fabsf(d);
+  const float a = (0.5f - v) * inv, b = (-0.5f - v) * inv;
+  const float p = std_cdf(a) - std_cdf(b);
+  const float k = 0.39894228040143267794f;
+  const float pa = __expf(-0.5f * a * a) * k, pb = __expf(-0.5f * b * b) * k;
+  *dp_dy = -signf_(d) * (pa - pb) * inv;
+  *dp_dsb = -(a * pa - b * pb) * inv;
+  *sigma_out = sigma;
+  return p;
+}
+
 __global__ void k_gauss_likelihood(const float* __restrict__ yt, const float* __restrict__ mu,
                                    const float* __restrict__ ls, long long numel, float* __restrict__ p_out,
                                    float* __restrict__ dpdy, float* __restrict__ dpdsb) {
@@ -260,7 +306,13 @@ __global__ void k_gauss_likelihood(const float* __restrict__ yt, const float* __
   if (dpdsb) dpdsb[e] = b;
 }
 
-template <typename AT>
+__device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store_pair(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// FAST (the bf16 loop): SFU-intrinsic soft round / Gaussian terms; the fp32 instantiation keeps the reference formulas
+template <typename AT, bool FAST = std::is_same<AT, __nv_bfloat16>::value>
 __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ inj, const float* __restrict__ h2,
                          int N, int Hy, int Wy, int Hh, int Wh, int C, float T, float eps, uint64_t seed, int step,
                          int hard, float rate_scale, AT* __restrict__ yt_act, float* __restrict__ g_rate,
@@ -285,36 +337,38 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
       const long long e0 = ((static_cast<long long>(n) * Hy + i) * Wy + j) * C + c;
       float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
       if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u, ctr_off);
+      // the pair (c, c+1) is contiguous in every tensor and c is even: 8-byte / 4-byte vector accesses
+      const float2 yv = *reinterpret_cast<const float2*>(y + e0);
+      const float2 muv = *reinterpret_cast<const float2*>(h2 + hpix * 2 * C + c);
+      const float2 lsv = *reinterpret_cast<const float2*>(h2 + hpix * 2 * C + C + c);
+      const float yk[2] = {yv.x, yv.y}, muk[2] = {muv.x, muv.y}, lsk[2] = {lsv.x, lsv.y};
+      float ytk[2], grk[2], dk[2], gmu[2], gls[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const long long e = e0 + k;
         float d = 0.0f, yt;
-        if (hard) yt = rintf(y[e]);
-        else yt = soft_round_one(y[e], u[2 * k], u[2 * k + 1], T, eps, &d);
-        const float mu = h2[hpix * 2 * C + c + k];
-        const float ls = h2[hpix * 2 * C + C + c + k];
+        if (hard) yt = rintf(yk[k]);
+        else yt = soft_round_sel<FAST>(yk[k], u[2 * k], u[2 * k + 1], T, eps, &d);
         float dpdy, dpdsb, sigma;
-        const float p = gauss_likelihood_one(yt, mu, ls, &dpdy, &dpdsb, &sigma);
+        const float p = FAST ? gauss_likelihood_fast(yt, muk[k], lsk[k], &dpdy, &dpdsb, &sigma)
+                             : gauss_likelihood_one(yt, muk[k], lsk[k], &dpdy, &dpdsb, &sigma);
         const float pc = fmaxf(p, 1e-9f);
-        nll += -logf(pc);
-        yt_act[e] = from_f32<AT>(yt);
-        if (g_rate) {
-          const float gp = -rate_scale / pc;  // upstream of p: always negative -> the likelihood bound passes it
-          g_rate[e] = gp * dpdy;
-          dy[e] = d;
-          const float gsb = gp * dpdsb;
-          // lower_bound(sigma, 0.11): pass iff sigma >= bound or gradient < 0 (math_ops.py:74-76)
-          const float gsig = (sigma >= 0.11f || gsb < 0.0f) ? gsb : 0.0f;
-          g_h2[hpix * 2 * C + c + k] = from_f32<AT>(-gp * dpdy);
-          g_h2[hpix * 2 * C + C + c + k] = from_f32<AT>(gsig * sigma);
-        }
+        nll += FAST ? -__logf(pc) : -logf(pc);
+        const float gp = FAST ? -rate_scale * __frcp_rn(pc) : -rate_scale / pc;  // upstream of p: always negative -> the bound passes it
+        const float gsb = gp * dpdsb;
+        // lower_bound(sigma, 0.11): pass iff sigma >= bound or gradient < 0 (math_ops.py:74-76)
+        const float gsig = (sigma >= 0.11f || gsb < 0.0f) ? gsb : 0.0f;
+        ytk[k] = yt; grk[k] = gp * dpdy; dk[k] = d; gmu[k] = -gp * dpdy; gls[k] = gsig * sigma;
+      }
+      store_pair(yt_act + e0, ytk[0], ytk[1]);
+      if (g_rate) {
+        *reinterpret_cast<float2*>(g_rate + e0) = make_float2(grk[0], grk[1]);
+        *reinterpret_cast<float2*>(dy + e0) = make_float2(dk[0], dk[1]);
+        store_pair(g_h2 + hpix * 2 * C + c, gmu[0], gmu[1]);
+        store_pair(g_h2 + hpix * 2 * C + C + c, gls[0], gls[1]);
       }
     } else if (g_h2) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        g_h2[hpix * 2 * C + c + k] = from_f32<AT>(0.0f);
-        g_h2[hpix * 2 * C + C + c + k] = from_f32<AT>(0.0f);
-      }
+      store_pair(g_h2 + hpix * 2 * C + c, 0.0f, 0.0f);
+      store_pair(g_h2 + hpix * 2 * C + C + c, 0.0f, 0.0f);
     }
   }
   const unsigned full = 0xffffffffu;
@@ -424,6 +478,41 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __re
   p[e] = __fsub_rn(p[e], __fdiv_rn(__fmul_rn(lr_t, mt), den));
   m[e] = mt;
   v[e] = vt;
+}
+
+// four elements per thread with 16-byte accesses (same per-element arithmetic and rounding order)
+__device__ __forceinline__ float adam_one(float g, float& p, float& m, float& v, float lr_t, float b1, float omb1, float b2,
+                                          float omb2, float eps) {
+  const float mt = __fadd_rn(__fmul_rn(b1, m), __fmul_rn(omb1, g));
+  const float vt = __fadd_rn(__fmul_rn(b2, v), __fmul_rn(omb2, __fmul_rn(g, g)));
+  const float den = __fadd_rn(__fsqrt_rn(vt), eps);
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, mt), den));
+  m = mt;
+  v = vt;
+  return g;
+}
+__global__ void k_adam_v4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
+                          const float* __restrict__ gb, const float* __restrict__ fac, long long numel4, float lr_t, float b1,
+                          float omb1, float b2, float omb2, float eps) {
+  const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (q >= numel4) return;
+  float4 g4 = reinterpret_cast<const float4*>(ga)[q];
+  if (gb) {
+    const float4 t = reinterpret_cast<const float4*>(gb)[q];
+    g4.x = __fadd_rn(g4.x, t.x); g4.y = __fadd_rn(g4.y, t.y); g4.z = __fadd_rn(g4.z, t.z); g4.w = __fadd_rn(g4.w, t.w);
+  }
+  if (fac) {
+    const float4 t = reinterpret_cast<const float4*>(fac)[q];
+    g4.x = __fmul_rn(g4.x, t.x); g4.y = __fmul_rn(g4.y, t.y); g4.z = __fmul_rn(g4.z, t.z); g4.w = __fmul_rn(g4.w, t.w);
+  }
+  float4 p4 = reinterpret_cast<float4*>(p)[q], m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+  adam_one(g4.x, p4.x, m4.x, v4.x, lr_t, b1, omb1, b2, omb2, eps);
+  adam_one(g4.y, p4.y, m4.y, v4.y, lr_t, b1, omb1, b2, omb2, eps);
+  adam_one(g4.z, p4.z, m4.z, v4.z, lr_t, b1, omb1, b2, omb2, eps);
+  adam_one(g4.w, p4.w, m4.w, v4.w, lr_t, b1, omb1, b2, omb2, eps);
+  reinterpret_cast<float4*>(p)[q] = p4;
+  reinterpret_cast<float4*>(m)[q] = m4;
+  reinterpret_cast<float4*>(v)[q] = v4;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -547,11 +636,23 @@ int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, 
   if (numel <= 0) return SGA_OK;
   const double t = iterations + 1.0;
   const double lr_t = lr * (sqrt(1.0 - pow(beta2, t)) / (1.0 - pow(beta1, t)));  // adam.py:40-42 (float64 scalar)
-  k_adam<<<blocks_for(numel, 256), 256, 0, st>>>(p, m, v, ga, gb, fac, numel, static_cast<float>(lr_t),
-                                                 static_cast<float>(beta1), static_cast<float>(1.0 - beta1),
-                                                 static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
-                                                 static_cast<float>(eps), g_out);
-  SGA_LAUNCH_CHECK();
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const float f_lr = static_cast<float>(lr_t), f_b1 = static_cast<float>(beta1), f_omb1 = static_cast<float>(1.0 - beta1),
+              f_b2 = static_cast<float>(beta2), f_omb2 = static_cast<float>(1.0 - beta2), f_eps = static_cast<float>(eps);
+  long long done = 0;
+  if (p != nullptr && g_out == nullptr && numel >= 4 && al16(p) && al16(m) && al16(v) && al16(ga) && al16(gb) && al16(fac)) {
+    const long long n4 = numel / 4;
+    k_adam_v4<<<blocks_for(n4, 256), 256, 0, st>>>(p, m, v, ga, gb, fac, n4, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps);
+    SGA_LAUNCH_CHECK();
+    done = n4 * 4;
+  }
+  if (done < numel) {   // tail (or everything: unaligned buffers, gradient-only calls)
+    k_adam<<<blocks_for(numel - done, 256), 256, 0, st>>>(p ? p + done : nullptr, m ? m + done : nullptr, v ? v + done : nullptr,
+                                                          ga + done, gb ? gb + done : nullptr, fac ? fac + done : nullptr,
+                                                          numel - done, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps,
+                                                          g_out ? g_out + done : nullptr);
+    SGA_LAUNCH_CHECK();
+  }
   return SGA_OK;
 }
 
