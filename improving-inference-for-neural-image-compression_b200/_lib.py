@@ -15,7 +15,7 @@ class SgaConfig(ctypes.Structure):
         ("num_filters", ctypes.c_int32), ("n_ref", ctypes.c_int32), ("operand", ctypes.c_int32),
         ("lmbda", ctypes.c_float), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
         ("adam_eps", ctypes.c_float), ("clip_eps", ctypes.c_float), ("seed", ctypes.c_uint64),
-        ("first_image", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("first_image", ctypes.c_int32), ("variant", ctypes.c_int32),
     ]
 
 
@@ -33,6 +33,9 @@ class SgaWeights(ctypes.Structure):
 
 OPERAND_F32 = 0
 OPERAND_BF16 = 1
+VARIANT_SGA = 0          # sga.py
+VARIANT_BITS_BACK = 1    # bb_sga.py
+BB_STATS_PER_IMAGE = 6
 STATS_HEADER = 3
 STATS_PER_IMAGE = 5
 PROF_LABELS = 24
@@ -46,6 +49,7 @@ EXPORTS = [
     "sga_bind_weights", "sga_encode_init", "sga_grad", "sga_step", "sga_eval_hard", "sga_reconstruction",
     "sga_launch_count", "sga_profile_enable", "sga_profile_read", "sga_op_soft_round",
     "sga_op_eb_likelihood", "sga_op_gauss_likelihood", "sga_op_adam", "sga_op_conv", "sga_op_gdn", "sga_op_igdn_bwd",
+    "sga_bb_hyper_init", "sga_bb_grad", "sga_bb_step", "sga_bb_eval",
 ]
 
 _lib = None
@@ -90,6 +94,10 @@ def load():
     lib.sga_op_conv.argtypes = [i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.sga_op_gdn.argtypes = [i32, i32, vp, vp, vp, i64, i32, vp, vp, vp]
     lib.sga_op_igdn_bwd.argtypes = [i32, vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.sga_bb_hyper_init.argtypes = [vp, vp, vp, vp, vp]
+    lib.sga_bb_grad.argtypes = [vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.sga_bb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, i32, f32, vp, vp]
+    lib.sga_bb_eval.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("sga_last_error", "sga_workspace_bytes", "sga_launch_count"):
             getattr(lib, name).restype = ctypes.c_int

@@ -30,6 +30,15 @@ struct ConvW {
   float* bias = nullptr;
 };
 
+// bits-back variant (bb_sga.py): how z_tilde is produced and which part of the graph is evaluated
+struct BbArgs {
+  const float* z_mean;
+  const float* z_logvar;
+  const float* eps;     // injected N(0,1) noise or nullptr -> Philox + Box-Muller
+  int rate_only;        // second loop (bb_sga.py:236-256): y_tilde fixed, loss = train_bpp, no synthesis transform
+  int y_hard;           // y holds y_tilde (already rounded) instead of y
+};
+
 struct Dims {
   int N, H, W, C, mid;
   int Hg[5], Wg[5];   // g_a pyramid: Hg[0]=H ... Hg[4]=Hy
@@ -64,6 +73,7 @@ struct sga_ctx {
   float *f_zt, *f_h0, *f_h1, *f_yt, *f_gh2, *f_xpre[3], *f_s[3], *f_act[3], *f_xt, *f_gx, *f_tmp, *f_nrm;
   float *f_ga[3], *f_gb[3], *f_gh1, *f_gh0;   // backward (only when cfg.operand == F32)
   float *f_init[2];                            // analysis scratch
+  float* bb_ha = nullptr;                      // bits-back variant: h_a output [n,hz,wz,2C] before the mean/logvar split
   // bf16 path
   bf16 *b_zt, *b_h0, *b_h1, *b_yt, *b_gh2, *b_xpre[3], *b_s[3], *b_act[3], *b_gx4, *b_ga[3], *b_gb[3], *b_gh1, *b_gh0;
   TcConv *tc_hs[3] = {0, 0, 0}, *tc_gs[3] = {0, 0, 0}, *tc_hs_d[3] = {0, 0, 0}, *tc_gs_d[3] = {0, 0, 0};
@@ -199,20 +209,32 @@ static int make_tc(int kind, const ConvW& w, int N, int Hin, int Win, const bf16
 // forward / backward, fp32 path
 // ---------------------------------------------------------------------------------------------------
 static int forward_f32(sga_ctx* c, const float* x, const float* y, const float* z, float T, int step, const float* ny,
-                       const float* nz, int hard, bool want_grad, float* stats, cudaStream_t st) {
+                       const float* nz, int hard, bool want_grad, float* stats, cudaStream_t st,
+                       const BbArgs* bb = nullptr) {
   const Dims& d = c->d;
   const sga_config& g = c->cfg;
   const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
-  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 4 * d.N * sizeof(double), st));
-  SGA_TRY(launch_z_path<float>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, hard, rate_scale,
-                               c->f_zt, want_grad ? c->gz_rate : nullptr, want_grad ? c->dz : nullptr, c->acc + d.N,
-                               g.first_image * (d.nz / d.N), st));
+  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 5 * d.N * sizeof(double), st));
+  if (bb) {
+    hard = bb->y_hard;
+    SGA_TRY(launch_zbb_path<float>(bb->z_mean, bb->z_logvar, bb->eps, d.nz, d.nz / d.N, d.C, c->eb_pack, g.seed, step,
+                                   rate_scale, c->f_zt, want_grad ? c->gz_rate : nullptr, want_grad ? c->dz : nullptr,
+                                   c->acc + d.N, c->acc + 4 * d.N, g.first_image * (d.nz / d.N), st));
+  } else {
+    SGA_TRY(launch_z_path<float>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, hard, rate_scale,
+                                 c->f_zt, want_grad ? c->gz_rate : nullptr, want_grad ? c->dz : nullptr, c->acc + d.N,
+                                 g.first_image * (d.nz / d.N), st));
+  }
   SGA_TRY(conv_f32(kUp2, c->hs[0], d.N, d.Hz, d.Wz, c->f_zt, true, 1, nullptr, c->f_h0, st));
   SGA_TRY(conv_f32(kUp2, c->hs[1], d.N, 2 * d.Hz, 2 * d.Wz, c->f_h0, true, 1, nullptr, c->f_h1, st));
   SGA_TRY(conv_f32(kS1True, c->hs[2], d.N, d.Hh, d.Wh, c->f_h1, true, 0, nullptr, c->h2, st));
   SGA_TRY(launch_y_path<float>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, hard,
                                rate_scale, c->f_yt, want_grad ? c->gy_rate : nullptr, want_grad ? c->dy : nullptr,
                                want_grad ? c->f_gh2 : nullptr, c->acc, g.first_image * (d.ny / d.N), st));
+  if (bb && bb->rate_only) {
+    if (stats) SGA_TRY(launch_finalize_stats_bb(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, 1, stats, st));
+    return SGA_OK;
+  }
   const float* in = c->f_yt;
   for (int i = 0; i < 3; ++i) {
     SGA_TRY(conv_f32(kUp2, c->gs[i], d.N, d.Hs[i], d.Ws[i], in, true, 0, nullptr, c->f_xpre[i], st));
@@ -227,14 +249,19 @@ static int forward_f32(sga_ctx* c, const float* x, const float* y, const float* 
                        : 0.0f;
   SGA_TRY(launch_distortion(x, c->f_xt, d.N, d.H, d.W, d.Hs[4], d.Ws[4], grad_scale, want_grad ? c->f_gx : nullptr,
                             c->acc + 2 * d.N, c->acc + 3 * d.N, st));
-  if (stats) SGA_TRY(launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
+  if (stats) {
+    if (bb) SGA_TRY(launch_finalize_stats_bb(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, 0, stats, st));
+    else SGA_TRY(launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
+  }
   return SGA_OK;
 }
 
-static int backward_f32(sga_ctx* c, cudaStream_t st) {
+static int backward_f32(sga_ctx* c, cudaStream_t st, bool rate_only = false) {
   const Dims& d = c->d;
   SGA_CHECK(c->f_ga[0] != nullptr, "context was created with operand=bf16: fp32 backward buffers are not allocated");
-  if (c->cfg.lmbda > 0.0f) {
+  if (rate_only) {
+    // y_tilde is fixed: only the hyper path carries gradient
+  } else if (c->cfg.lmbda > 0.0f) {
     SGA_TRY(conv_f32(kUp2Dgrad, c->gs[3], d.N, d.Hs[4], d.Ws[4], c->f_gx, false, 0, nullptr, c->f_ga[2], st));
     for (int i = 2; i >= 0; --i) {
       const long long pix = static_cast<long long>(d.N) * d.Hs[i + 1] * d.Ws[i + 1];
@@ -256,19 +283,28 @@ static int backward_f32(sga_ctx* c, cudaStream_t st) {
 // forward + backward, bf16 tcgen05 path
 // ---------------------------------------------------------------------------------------------------
 static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, const float* z, float T, int step,
-                                 const float* ny, const float* nz, float* stats, cudaStream_t st) {
+                                 const float* ny, const float* nz, float* stats, cudaStream_t st,
+                                 const BbArgs* bb = nullptr) {
   const Dims& d = c->d;
   const sga_config& g = c->cfg;
   const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
-  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 4 * d.N * sizeof(double), st));
+  const bool rate_only = bb && bb->rate_only;
+  const int y_hard = bb ? bb->y_hard : 0;
+  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 5 * d.N * sizeof(double), st));
+  if (bb) {
+    PROF(c, SGA_PROF_ELEMENTWISE, st, launch_zbb_path<bf16>(bb->z_mean, bb->z_logvar, bb->eps, d.nz, d.nz / d.N, d.C, c->eb_pack, g.seed,
+                                step, rate_scale, c->b_zt, c->gz_rate, c->dz, c->acc + d.N, c->acc + 4 * d.N,
+                                g.first_image * (d.nz / d.N), st));
+  } else {
   PROF(c, SGA_PROF_ELEMENTWISE, st, launch_z_path<bf16>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, 0, rate_scale,
                               c->b_zt, c->gz_rate, c->dz, c->acc + d.N, g.first_image * (d.nz / d.N), st));
+  }
   PROF(c, SGA_PROF_CONV_HS + 0, st, tc_conv_launch(c->tc_hs[0], c->hs[0].bias, 1, nullptr, c->b_h0, nullptr, st));
   PROF(c, SGA_PROF_CONV_HS + 1, st, tc_conv_launch(c->tc_hs[1], c->hs[1].bias, 1, nullptr, c->b_h1, nullptr, st));
   PROF(c, SGA_PROF_CONV_HS + 2, st, tc_conv_launch(c->tc_hs[2], c->hs[2].bias, 0, nullptr, nullptr, c->h2, st));
-  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_y_path<bf16>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, 0,
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_y_path<bf16>(y, ny, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps, g.seed, step, y_hard,
                               rate_scale, c->b_yt, c->gy_rate, c->dy, c->b_gh2, c->acc, g.first_image * (d.ny / d.N), st));
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 3 && !rate_only; ++i) {
     if (c->fused) {
       PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch_igdn_fwd(c->tc_gs[i], c->gs[i].bias, c->gs_beta[i], c->b_s[i],
                                                                 c->b_act[i], st));
@@ -280,11 +316,17 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   const float grad_scale =
       (g.lmbda > 0.0f) ? static_cast<float>(2.0 * 65025.0 * g.lmbda / (static_cast<double>(g.n_ref) * d.H * d.W * 3.0))
                        : 0.0f;
-  PROF(c, SGA_PROF_L3_FWD, st, l3_tc_forward(c->l3, c->gs3_bias_host, x, grad_scale, nullptr, c->b_gx4, c->acc + 2 * d.N, c->acc + 3 * d.N,
-                        st));
-  if (stats) PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
+  if (!rate_only)
+    PROF(c, SGA_PROF_L3_FWD, st, l3_tc_forward(c->l3, c->gs3_bias_host, x, grad_scale, nullptr, c->b_gx4, c->acc + 2 * d.N, c->acc + 3 * d.N,
+                          st));
+  if (stats) {
+    if (bb) PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats_bb(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, rate_only ? 1 : 0, stats, st));
+    else PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda, stats, st));
+  }
   // ---- backward
-  if (g.lmbda > 0.0f) {
+  if (rate_only) {
+    // y_tilde is fixed: only the hyper path carries gradient
+  } else if (g.lmbda > 0.0f) {
     if (c->fused) {
       // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
       // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
@@ -313,6 +355,7 @@ static int grad_common(sga_ctx* c, const float* x, const float* y, const float* 
                        const float* nz, float* stats, cudaStream_t st) {
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
   SGA_CHECK(T > 0.0f, "temperature must be positive");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are driven through sga_bb_grad / sga_bb_step");
   if (c->cfg.operand == SGA_OPERAND_BF16) return forward_backward_bf16(c, x, y, z, T, step, ny, nz, stats, st);
   SGA_TRY(forward_f32(c, x, y, z, T, step, ny, nz, 0, true, stats, st));
   return backward_f32(c, st);
@@ -335,6 +378,7 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
   SGA_CHECK(cfg->n_ref >= 1, "n_ref must be >= 1");
   SGA_CHECK(cfg->first_image >= 0, "first_image must be >= 0");
   SGA_CHECK(cfg->operand == SGA_OPERAND_F32 || cfg->operand == SGA_OPERAND_BF16, "unknown operand type");
+  SGA_CHECK(cfg->variant == SGA_VARIANT_SGA || cfg->variant == SGA_VARIANT_BITS_BACK, "unknown variant %d", cfg->variant);
   if (cfg->operand == SGA_OPERAND_BF16)
     SGA_CHECK(cfg->num_filters % 64 == 0 && cfg->num_filters <= 256,
               "the bf16 tcgen05 path needs num_filters %% 64 == 0 and <= 256 (got %d)", cfg->num_filters);
@@ -349,7 +393,8 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
   const long long nh2 = static_cast<long long>(d.N) * d.Hh * d.Wh * 2 * d.C;
   const long long nxt = static_cast<long long>(d.N) * d.Hs[4] * d.Ws[4] * 3;
   const long long e3 = gs_elems(d, 3);
-  A(&c->acc, 4 * d.N);
+  A(&c->acc, 5 * d.N);
+  if (cfg->variant == SGA_VARIANT_BITS_BACK) A(&c->bb_ha, 2 * d.nz);
   A(&c->dz, d.nz); A(&c->gz_rate, d.nz); A(&c->gz_hyper, d.nz);
   A(&c->dy, d.ny); A(&c->gy_rate, d.ny); A(&c->gy_dist, d.ny);
   A(&c->h2, nh2);
@@ -418,7 +463,8 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
   for (int i = 0; i < 4; ++i) SGA_TRY(bind_conv(c, c->gs[i], w->gs_kernel[i], w->gs_bias[i], 5, 5, C, gs_co[i], bf && i < 3, st));
   SGA_TRY(bind_conv(c, c->ha[0], w->ha_kernel[0], w->ha_bias[0], 3, 3, C, C, false, st));
   SGA_TRY(bind_conv(c, c->ha[1], w->ha_kernel[1], w->ha_bias[1], 5, 5, C, C, false, st));
-  SGA_TRY(bind_conv(c, c->ha[2], w->ha_kernel[2], nullptr, 5, 5, C, C, false, st));
+  // bits-back variant: h_a emits 2C channels, z_mean | z_logvar (bb_sga.py:69,99)
+  SGA_TRY(bind_conv(c, c->ha[2], w->ha_kernel[2], nullptr, 5, 5, C, c->cfg.variant == SGA_VARIANT_BITS_BACK ? 2 * C : C, false, st));
   SGA_TRY(bind_conv(c, c->hs[0], w->hs_kernel[0], w->hs_bias[0], 5, 5, C, C, bf, st));
   SGA_TRY(bind_conv(c, c->hs[1], w->hs_kernel[1], w->hs_bias[1], 5, 5, C, d.mid, bf, st));
   SGA_TRY(bind_conv(c, c->hs[2], w->hs_kernel[2], w->hs_bias[2], 3, 3, d.mid, 2 * C, bf, st));
@@ -492,10 +538,85 @@ int sga_encode_init(sga_ctx* c, const float* x, float* y_out, float* z_out, void
     }
   }
   // h_a: 3x3 s1 ReLU, 5x5 s2 ReLU, 5x5 s2 without bias (nn_models.py:84-103)
+  if (c->cfg.variant == SGA_VARIANT_BITS_BACK) {
+    SGA_CHECK(z_out == nullptr, "bits-back variant: z_mean / z_logvar come from sga_bb_hyper_init (pass z_out = NULL)");
+    return SGA_OK;
+  }
   SGA_TRY(conv_f32(kS1Corr, c->ha[0], d.N, d.Hy, d.Wy, y_out, true, 1, nullptr, c->f_init[0], st));
   SGA_TRY(conv_f32(kDown2Corr, c->ha[1], d.N, d.Hy, d.Wy, c->f_init[0], true, 1, nullptr, c->f_init[1], st));
   SGA_TRY(conv_f32(kDown2Corr, c->ha[2], d.N, d.Hz1, d.Wz1, c->f_init[1], false, 0, nullptr, z_out, st));
   return SGA_OK;
+}
+
+// ---- bits-back variant (reference bb_sga.py) ---------------------------------------------------------------------
+
+int sga_bb_hyper_init(sga_ctx* c, const float* y_tilde, float* z_mean_out, float* z_logvar_out, void* stream) {
+  SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_BITS_BACK, "context was not created with variant = SGA_VARIANT_BITS_BACK");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dims& d = c->d;
+  SGA_TRY(conv_f32(kS1Corr, c->ha[0], d.N, d.Hy, d.Wy, y_tilde, true, 1, nullptr, c->f_init[0], st));
+  SGA_TRY(conv_f32(kDown2Corr, c->ha[1], d.N, d.Hy, d.Wy, c->f_init[0], true, 1, nullptr, c->f_init[1], st));
+  SGA_TRY(conv_f32(kDown2Corr, c->ha[2], d.N, d.Hz1, d.Wz1, c->f_init[1], false, 0, nullptr, c->bb_ha, st));
+  return launch_split2(c->bb_ha, d.nz / d.C, d.C, z_mean_out, z_logvar_out, st);
+}
+
+static int bb_grad_common(sga_ctx* c, const float* x, const float* y, const BbArgs& bb, float T, int step, const float* ny,
+                          float* stats, cudaStream_t st) {
+  SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_BITS_BACK, "context was not created with variant = SGA_VARIANT_BITS_BACK");
+  SGA_CHECK(bb.rate_only || T > 0.0f, "temperature must be positive");
+  const Dims& d = c->d;
+  if (c->cfg.operand == SGA_OPERAND_BF16) {
+    SGA_TRY(forward_backward_bf16(c, x, y, nullptr, T, step, ny, nullptr, stats, st, &bb));
+  } else {
+    SGA_TRY(forward_f32(c, x, y, nullptr, T, step, ny, nullptr, 0, true, stats, st, &bb));
+    SGA_TRY(backward_f32(c, st, bb.rate_only != 0));
+  }
+  // g_mean -> gz_rate, g_logvar -> dz (in place)
+  const float half_scale = static_cast<float>(0.5 / (log(2.0) * d.H * static_cast<double>(d.W) * c->cfg.n_ref));
+  return launch_bb_grads(c->gz_rate, c->gz_hyper, c->dz, d.nz, half_scale, c->gz_rate, c->dz, st);
+}
+
+int sga_bb_grad(sga_ctx* c, const float* x, const float* y, const float* z_mean, const float* z_logvar, float T,
+                int32_t step, const float* noise_y, const float* eps_z, int32_t rate_only, float* grad_y,
+                float* grad_z_mean, float* grad_z_logvar, float* stats, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BbArgs bb{z_mean, z_logvar, eps_z, rate_only ? 1 : 0, rate_only ? 1 : 0};
+  SGA_TRY(bb_grad_common(c, x, y, bb, T, step, noise_y, stats, st));
+  const sga_config& g = c->cfg;
+  if (!rate_only && grad_y)
+    SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1, g.beta2,
+                        g.adam_eps, 0, grad_y, st));
+  SGA_CUDA(cudaMemcpyAsync(grad_z_mean, c->gz_rate, c->d.nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SGA_CUDA(cudaMemcpyAsync(grad_z_logvar, c->dz, c->d.nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SGA_OK;
+}
+
+int sga_bb_step(sga_ctx* c, const float* x, float* y, float* z_mean, float* z_logvar, float* m_y, float* v_y, float* m_zm,
+                float* v_zm, float* m_zl, float* v_zl, float T, int32_t step, int32_t adam_iterations, const float* noise_y,
+                const float* eps_z, int32_t rate_only, float lr, float* stats, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BbArgs bb{z_mean, z_logvar, eps_z, rate_only ? 1 : 0, rate_only ? 1 : 0};
+  SGA_TRY(bb_grad_common(c, x, y, bb, T, step, noise_y, stats, st));
+  const sga_config& g = c->cfg;
+  if (!rate_only)
+    SGA_TRY(launch_adam(y, m_y, v_y, c->gy_rate, c->gy_dist, c->dy, c->d.ny, lr, g.beta1, g.beta2, g.adam_eps, adam_iterations,
+                        nullptr, st));
+  SGA_TRY(launch_adam(z_mean, m_zm, v_zm, c->gz_rate, nullptr, nullptr, c->d.nz, lr, g.beta1, g.beta2, g.adam_eps, adam_iterations,
+                      nullptr, st));
+  SGA_TRY(launch_adam(z_logvar, m_zl, v_zl, c->dz, nullptr, nullptr, c->d.nz, lr, g.beta1, g.beta2, g.adam_eps, adam_iterations,
+                      nullptr, st));
+  return SGA_OK;
+}
+
+int sga_bb_eval(sga_ctx* c, const float* x, const float* y_tilde, const float* z_mean, const float* z_logvar,
+                int32_t step, const float* eps_z, float* stats, void* stream) {
+  SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_BITS_BACK, "context was not created with variant = SGA_VARIANT_BITS_BACK");
+  const BbArgs bb{z_mean, z_logvar, eps_z, 0, 1};
+  return forward_f32(c, x, y_tilde, nullptr, 1.0f, step, nullptr, nullptr, 1, false, stats, static_cast<cudaStream_t>(stream),
+                     &bb);
 }
 
 int sga_grad(sga_ctx* c, const float* x, const float* y, const float* z, float T, int32_t step, const float* ny,
@@ -524,6 +645,7 @@ int sga_step(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* 
 
 int sga_eval_hard(sga_ctx* c, const float* x, const float* y, const float* z, float* stats, void* stream) {
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are evaluated through sga_bb_eval");
   return forward_f32(c, x, y, z, 1.0f, 0, nullptr, nullptr, 1, false, stats, static_cast<cudaStream_t>(stream));
 }
 

@@ -254,6 +254,159 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// bits-back variant (bb_sga.py:99-111, 132-141): z_tilde = eps*exp(logvar/2) + mean, rate under the DENSITY of the
+// flexible prior (learned_prior.py:296-347: product of the layer Jacobians times sigmoid'), bits-back term log q.
+// The density's slope needs the second derivative of the CDF network: forward mode, second order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void eb_gate2(float f, float& a, float& a1, float& a2) {
+  // y = a + f tanh(a):  y' = a'(1 + f(1-t^2)),  y'' = a''(1 + f(1-t^2)) - 2 f t (1-t^2) a'^2
+  const float t = tanhf(a);
+  const float q = 1.0f - t * t;
+  const float gate = 1.0f + f * q;
+  a2 = a2 * gate - 2.0f * f * t * q * a1 * a1;
+  a1 = a1 * gate;
+  a = a + f * t;
+}
+__device__ __forceinline__ void eb_logit2(const EbParams& P, float u, float* L, float* L1, float* L2) {
+  float h[3], d[3], dd[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    h[r] = P.p[r] * u + P.p[3 + r];
+    d[r] = P.p[r];
+    dd[r] = 0.0f;
+    eb_gate2(P.p[6 + r], h[r], d[r], dd[r]);
+  }
+#pragma unroll
+  for (int layer = 0; layer < 2; ++layer) {
+    const int mo = 9 + 15 * layer, bo = 18 + 15 * layer, fo = 21 + 15 * layer;
+    float h2[3], d2[3], dd2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float a = P.p[bo + r], g = 0.0f, gg = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a += P.p[mo + r * 3 + k] * h[k];
+        g += P.p[mo + r * 3 + k] * d[k];
+        gg += P.p[mo + r * 3 + k] * dd[k];
+      }
+      eb_gate2(P.p[fo + r], a, g, gg);
+      h2[r] = a; d2[r] = g; dd2[r] = gg;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { h[r] = h2[r]; d[r] = d2[r]; dd[r] = dd2[r]; }
+  }
+  float a = P.p[42], g = 0.0f, gg = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { a += P.p[39 + k] * h[k]; g += P.p[39 + k] * d[k]; gg += P.p[39 + k] * dd[k]; }
+  *L = a; *L1 = g; *L2 = gg;
+}
+
+template <typename AT>
+__global__ void k_zbb_path(const float* __restrict__ z_mean, const float* __restrict__ z_logvar,
+                           const float* __restrict__ eps_inj, long long numel, long long per_image, int C,
+                           const float* __restrict__ pk, uint64_t seed, int step, float rate_scale, AT* __restrict__ zt_act,
+                           float* __restrict__ g_zt, float* __restrict__ dzl, double* __restrict__ bits,
+                           double* __restrict__ logq, long long ctr_off) {
+  const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long e0 = pair * 2;
+  float nll = 0.0f, lq = 0.0f;
+  long long img = -1;
+  if (e0 < numel) {
+    img = e0 / per_image;
+    float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    if (eps_inj == nullptr) pair_uniforms(nullptr, numel, e0, seed, step, TENSOR_ID_EPS, u, ctr_off);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long e = e0 + k;
+      if (e < numel) {
+        // Box-Muller: eps = sqrt(-2 ln u0) cos(2 pi u1)   (oracle/bb_oracle.py normal_from_uniforms)
+        const float eps = eps_inj ? eps_inj[e] : sqrtf(-2.0f * logf(u[2 * k])) * cosf(6.283185307179586f * u[2 * k + 1]);
+        const float lv = z_logvar[e];
+        const float sd = expf(0.5f * lv);
+        const float zt = eps * sd + z_mean[e];
+        EbParams P;
+        eb_load(pk, C, static_cast<int>(e % C), P);
+        float L, L1, L2;
+        eb_logit2(P, zt, &L, &L1, &L2);
+        const float sg = sigmoidf_(L);
+        const float w = sg * (1.0f - sg);
+        const float pdf = w * L1;
+        const float dpdf = w * ((1.0f - 2.0f * sg) * L1 * L1 + L2);
+        const float pc = fmaxf(pdf, 1e-9f);                      // lower_bound: the (negative) upstream gradient always passes
+        nll += -logf(pc);
+        const float r = zt - z_mean[e];
+        lq += -0.5f * (r * r * expf(-lv) + lv + 1.8378770664093453f);   // utils.py:75-77
+        zt_act[e] = from_f32<AT>(zt);
+        if (g_zt) g_zt[e] = (-rate_scale / pc) * dpdf;
+        if (dzl) dzl[e] = 0.5f * eps * sd;                       // d z_tilde / d logvar
+      }
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const long long img0 = __shfl_sync(full, img, 0);
+  const bool uniform = __all_sync(full, img == img0);
+  if (uniform) {
+    const float s = warp_sum(nll), q = warp_sum(lq);
+    if ((threadIdx.x & 31) == 0 && img0 >= 0) {
+      atomicAdd(bits + img0, static_cast<double>(s));
+      atomicAdd(logq + img0, static_cast<double>(q));
+    }
+  } else if (img >= 0) {
+    atomicAdd(bits + img, static_cast<double>(nll));
+    atomicAdd(logq + img, static_cast<double>(lq));
+  }
+}
+
+// g_mean = g_zt_rate + g_hyper;  g_logvar = g_mean * dz_tilde/dlogvar - rate_scale/2   (d log q / d logvar = -1/2 enters
+// the loss with +rate_scale: eval_bpp = ... - bpp_back, bpp_back = -sum log q / (ln2 HW))
+__global__ void k_bb_grads(const float* __restrict__ g_rate, const float* __restrict__ g_hyper, const float* __restrict__ dzl,
+                           long long numel, float half_scale, float* __restrict__ g_mean, float* __restrict__ g_lv) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= numel) return;
+  const float g = g_rate[e] + g_hyper[e];
+  const float d = dzl[e];
+  g_mean[e] = g;
+  g_lv[e] = g * d - half_scale;
+}
+
+// [pixels, 2C] -> two [pixels, C] tensors (z_mean | z_logvar, bb_sga.py:99)
+__global__ void k_split2(const float* __restrict__ in, long long pixels, int C, float* __restrict__ a, float* __restrict__ b) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= pixels * C) return;
+  const long long p = e / C;
+  const int c = static_cast<int>(e % C);
+  a[e] = in[p * 2 * C + c];
+  b[e] = in[p * 2 * C + C + c];
+}
+
+// bits-back statistics: rd_loss, train_mse, train_bpp, then per image psnr, y_bpp, z_bpp, sse, mse_rounded, bpp_back
+__global__ void k_finalize_stats_bb(const double* __restrict__ acc, int N, int n_ref, int H, int W, float lmbda,
+                                    int rate_only, float* __restrict__ out) {
+  // acc: [0,N) y nats, [N,2N) z nats, [2N,3N) sse, [3N,4N) sse rounded, [4N,5N) sum log q
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double npix = static_cast<double>(H) * W;
+  const double ln2 = 0.69314718055994530942;
+  double bpp_sum = 0.0, sse_sum = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const double yb = acc[n] / (ln2 * npix), zb = acc[N + n] / (ln2 * npix), back = -acc[4 * N + n] / (ln2 * npix);
+    const double mse_r = acc[3 * N + n] / (npix * 3.0);
+    out[3 + 6 * n + 0] = rate_only ? 0.0f : static_cast<float>(20.0 * log10(255.0) - 10.0 * log10(mse_r));
+    out[3 + 6 * n + 1] = static_cast<float>(yb);
+    out[3 + 6 * n + 2] = static_cast<float>(zb);
+    out[3 + 6 * n + 3] = static_cast<float>(acc[2 * N + n]);
+    out[3 + 6 * n + 4] = static_cast<float>(mse_r);
+    out[3 + 6 * n + 5] = static_cast<float>(back);
+    bpp_sum += yb + zb - back;
+    sse_sum += acc[2 * N + n];
+  }
+  const double train_mse = sse_sum / (static_cast<double>(n_ref) * npix * 3.0) * 65025.0;
+  const double train_bpp = bpp_sum / n_ref;
+  out[0] = static_cast<float>((lmbda > 0.0f && !rate_only) ? lmbda * train_mse + train_bpp : train_bpp);
+  out[1] = static_cast<float>(train_mse);
+  out[2] = static_cast<float>(train_bpp);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1(y)+K4: soft round of y fused with the Gaussian-conditional rate.  Iterates over the pixel grid of
 // h2 = h_s(z_tilde) [N,Hh,Wh,2C]; pixels outside y's grid (the crop of sga.py:126-128) get zero gradient.
 // ------------------------------------------------------------------------------------------------
@@ -621,6 +774,44 @@ int launch_distortion(const float* x, const float* xt, int N, int H, int W, int 
                       double* sse, double* sse_r, cudaStream_t st) {
   const long long npix = static_cast<long long>(N) * Ho * Wo;
   k_distortion<<<blocks_for(npix, 256), 256, 0, st>>>(x, xt, N, H, W, Ho, Wo, grad_scale, gx, sse, sse_r);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+template <typename AT>
+int launch_zbb_path(const float* z_mean, const float* z_logvar, const float* eps_inj, long long numel, long long per_image,
+                    int C, const float* pk, uint64_t seed, int step, float rate_scale, AT* zt_act, float* g_zt, float* dzl,
+                    double* bits, double* logq, long long ctr_off, cudaStream_t st) {
+  const long long pairs = (numel + 1) / 2;
+  k_zbb_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(z_mean, z_logvar, eps_inj, numel, per_image, C, pk, seed, step,
+                                                         rate_scale, zt_act, g_zt, dzl, bits, logq, ctr_off);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+template int launch_zbb_path<float>(const float*, const float*, const float*, long long, long long, int, const float*,
+                                    uint64_t, int, float, float*, float*, float*, double*, double*, long long, cudaStream_t);
+template int launch_zbb_path<__nv_bfloat16>(const float*, const float*, const float*, long long, long long, int,
+                                            const float*, uint64_t, int, float, __nv_bfloat16*, float*, float*, double*,
+                                            double*, long long, cudaStream_t);
+
+int launch_bb_grads(const float* g_rate, const float* g_hyper, const float* dzl, long long numel, float half_scale,
+                    float* g_mean, float* g_lv, cudaStream_t st) {
+  if (numel <= 0) return SGA_OK;
+  k_bb_grads<<<blocks_for(numel, 256), 256, 0, st>>>(g_rate, g_hyper, dzl, numel, half_scale, g_mean, g_lv);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_split2(const float* in, long long pixels, int C, float* a, float* b, cudaStream_t st) {
+  if (pixels <= 0) return SGA_OK;
+  k_split2<<<blocks_for(pixels * C, 256), 256, 0, st>>>(in, pixels, C, a, b);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+int launch_finalize_stats_bb(const double* acc, int N, int n_ref, int H, int W, float lmbda, int rate_only, float* out,
+                             cudaStream_t st) {
+  k_finalize_stats_bb<<<1, 32, 0, st>>>(acc, N, n_ref, H, W, lmbda, rate_only, out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

@@ -6,6 +6,7 @@ namespace sga {
 
 constexpr int TENSOR_ID_Y = 1;  // Philox counter word 2 (oracle/sga_oracle.py TENSOR_ID_*)
 constexpr int TENSOR_ID_Z = 2;
+constexpr int TENSOR_ID_EPS = 3;  // bits-back variant: the Gaussian noise of z_tilde (oracle/bb_oracle.py)
 
 // ---- elementwise.cu
 int launch_soft_round(const float* v, const float* inj, long long numel, float T, float eps, uint64_t seed, int step,
@@ -23,6 +24,16 @@ template <typename AT>
 int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
                   float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st);
+// bits-back variant (bb_sga.py): z_tilde = eps*exp(logvar/2) + mean, prior density + slope, log q; see elementwise.cu
+template <typename AT>
+int launch_zbb_path(const float* z_mean, const float* z_logvar, const float* eps_inj, long long numel, long long per_image,
+                    int C, const float* pk, uint64_t seed, int step, float rate_scale, AT* zt_act, float* g_zt, float* dzl,
+                    double* bits, double* logq, long long ctr_off, cudaStream_t st);
+int launch_bb_grads(const float* g_rate, const float* g_hyper, const float* dzl, long long numel, float half_scale,
+                    float* g_mean, float* g_lv, cudaStream_t st);
+int launch_split2(const float* in, long long pixels, int C, float* a, float* b, cudaStream_t st);
+int launch_finalize_stats_bb(const double* acc, int N, int n_ref, int H, int W, float lmbda, int rate_only, float* out,
+                             cudaStream_t st);
 int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
                       double* sse, double* sse_r, cudaStream_t st);
 int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st);

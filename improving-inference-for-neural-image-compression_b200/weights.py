@@ -110,6 +110,41 @@ def make_synthetic(C, seed=0):
     return W
 
 
+# ---- bits-back variant (bb_sga.py / mbt2018_bb.py) ------------------------------------------------------------------
+PRIOR = "bmsh_j2018prior/"       # Keras snake-case of learned_prior.BMSHJ2018Prior (bb_sga.py:63)
+
+
+def variable_shapes_bb(C):
+    """bb_sga.py:63-70: h_a emits 2C channels (z_mean | z_logvar, bb_sga.py:99) and the hyperprior density is the
+    BMSHJ2018Prior model (same per-channel network as the EntropyBottleneck, learned_prior.py:43-66)."""
+    s = {k: v for k, v in variable_shapes(C).items() if not k.startswith(EB)}
+    s[(HA % 2) + "kernel"] = (5, 5, C, 2 * C)
+    dims = (1, 3, 3, 3, 1)
+    for i in range(4):
+        s[PRIOR + "matrix_%d" % i] = (C, dims[i + 1], dims[i])
+        s[PRIOR + "bias_%d" % i] = (C, dims[i + 1], 1)
+        if i < 3:
+            s[PRIOR + "factor_%d" % i] = (C, dims[i + 1], 1)
+    return s
+
+
+def make_synthetic_bb(C, seed=0):
+    """Synthetic weights of the bits-back model: the mean-scale weights of make_synthetic with the prior renamed and a
+    2C-channel last h_a layer whose log-variance half is shifted to give posterior standard deviations around 0.3."""
+    W0 = make_synthetic(C, seed)
+    rng = np.random.default_rng(seed + 12345)
+    W = {}
+    for k, v in W0.items():
+        if k.startswith(EB):
+            W[PRIOR + k[len(EB):]] = v
+        elif k == (HA % 2) + "kernel":
+            extra = (rng.standard_normal(v.shape) * (0.3 * v.std())).astype(np.float32)
+            W[k] = np.concatenate([v, extra], axis=-1)
+        else:
+            W[k] = v
+    return W
+
+
 # ---- re-parameterisations used by the reference's checkpoints -------------------------------------------
 
 def gdn_from_reparam(reparam, minimum):
@@ -176,8 +211,8 @@ def deparameterise(raw):
     return W
 
 
-def check_complete(W, C):
-    want = variable_shapes(C)
+def check_complete(W, C, bb=False):
+    want = variable_shapes_bb(C) if bb else variable_shapes(C)
     missing = [k for k in want if k not in W]
     if missing:
         raise KeyError("checkpoint is missing variables: %s" % ", ".join(missing[:6]))
@@ -196,7 +231,7 @@ def save_checkpoint(checkpoint_dir, runname, W):
     return path
 
 
-def load_checkpoint(checkpoint_dir, runname, num_filters):
+def load_checkpoint(checkpoint_dir, runname, num_filters, bb=False):
     """Mirror of tf.train.latest_checkpoint + Saver.restore (sga.py:180-182)."""
     d = os.path.join(checkpoint_dir, runname)
     path = os.path.join(d, "model.npz")
@@ -207,7 +242,7 @@ def load_checkpoint(checkpoint_dir, runname, num_filters):
     with np.load(path) as f:
         raw = {k: f[k] for k in f.files}
     W = deparameterise(raw)
-    check_complete(W, num_filters)
+    check_complete(W, num_filters, bb=bb)
     return W
 
 

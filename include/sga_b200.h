@@ -40,6 +40,12 @@ typedef enum {
   SGA_OPERAND_BF16 = 1   /* bf16 operands, fp32 accumulate in TMEM: tcgen05 implicit-GEMM kernels */
 } sga_operand;
 
+/* which per-iteration graph the context evaluates */
+typedef enum {
+  SGA_VARIANT_SGA = 0,        /* sga.py: Gumbel soft round of y and z, factorised-prior likelihood of z */
+  SGA_VARIANT_BITS_BACK = 1   /* bb_sga.py: z_tilde = eps*exp(logvar/2)+mean, prior density, bits-back term; h_a has 2C outputs */
+} sga_variant;
+
 typedef struct {
   int32_t n_images;        /* images resident on this GPU (the shard) */
   int32_t height, width;   /* image size (sga.py:51) */
@@ -53,7 +59,7 @@ typedef struct {
   uint64_t seed;           /* key of the Philox4x32-10 Gumbel noise stream */
   int32_t first_image;     /* index of this shard's first image inside the reference batch: the noise counter is the
                               element index inside the WHOLE batch, so results do not depend on the sharding */
-  int32_t reserved_;
+  int32_t variant;         /* sga_variant: which reference script's graph (0 = sga.py, 1 = bb_sga.py) */
 } sga_config;
 
 /* Weights in the reference's variable layout (float32 device pointers; kernels (kh,kw,Cin,Cout),
@@ -111,6 +117,36 @@ int sga_eval_hard(sga_ctx* ctx, const float* x, const float* y, const float* z, 
 /* Copies the cropped reconstruction x_tilde [n,H,W,3] (float, un-clipped) of the most recent fp32 forward
  * (sga_eval_hard, or sga_grad/sga_step with operand f32) -- used for MS-SSIM (sga.py:175) and PNG dumps. */
 int sga_reconstruction(sga_ctx* ctx, float* xt_out, void* stream);
+
+/* ---- bits-back variant (reference bb_sga.py) -- contexts created with variant = SGA_VARIANT_BITS_BACK -------------
+ * The weights struct is the same; ha_kernel[2] is (5,5,C,2C) (bb_sga.py:69) and eb_* hold the BMSHJ2018Prior
+ * variables (bb_sga.py:63; same per-channel network, learned_prior.py:43-66).  sga_encode_init is called with
+ * z_out = NULL.  Statistics: [0] rd_loss [1] train_mse [2] train_bpp (= mean of y_bpp + z_bpp - bpp_back), then per
+ * image [3+6n] psnr [4+6n] y_bpp [5+6n] z_bpp [6+6n] sse [7+6n] rounded mse [8+6n] bpp_back  -> 3 + 6*n_images floats. */
+#define SGA_BB_STATS_PER_IMAGE 6
+
+/* (z_mean_init, z_logvar_init) = split(h_a(y_tilde))   bb_sga.py:99, 204, 247.  Always fp32. */
+int sga_bb_hyper_init(sga_ctx* ctx, const float* y_tilde, float* z_mean_out, float* z_logvar_out, void* stream);
+
+/* One evaluation of bb_sga.py's per-iteration graph: gradients w.r.t. [y, z_mean, z_logvar] of rd_loss
+ * (bb_sga.py:156, 212-216), or -- rate_only != 0 -- w.r.t. [z_mean, z_logvar] of train_bpp with `y` holding the fixed
+ * y_tilde = round(y) (bb_sga.py:157, 250-252; x may be NULL, grad_y is not written).  eps_z: injected N(0,1) noise
+ * shaped like z_mean, or NULL -> Philox(seed, step, tensor 3) + Box-Muller. */
+int sga_bb_grad(sga_ctx* ctx, const float* x, const float* y, const float* z_mean, const float* z_logvar,
+                float temperature, int32_t step, const float* noise_y, const float* eps_z, int32_t rate_only,
+                float* grad_y, float* grad_z_mean, float* grad_z_logvar, float* stats_out, void* stream);
+
+/* sga_bb_grad followed by adam.py's update (one optimiser over the tensors, bb_sga.py:208,217 / :248,253) with
+ * learning rate `lr` (0.005 in the R-D loop, 0.003 in the rate loop; bb_sga.py:186,192).  `step` keys the noise,
+ * `adam_iterations` is the optimiser's 0-based iteration count (it restarts with the second loop). */
+int sga_bb_step(sga_ctx* ctx, const float* x, float* y, float* z_mean, float* z_logvar, float* m_y, float* v_y,
+                float* m_zm, float* v_zm, float* m_zl, float* v_zl, float temperature, int32_t step,
+                int32_t adam_iterations, const float* noise_y, const float* eps_z, int32_t rate_only, float lr,
+                float* stats_out, void* stream);
+
+/* eval_tensors of bb_sga.py:176-177 for y_tilde = round(y) (bb_sga.py:271-272), always fp32. */
+int sga_bb_eval(sga_ctx* ctx, const float* x, const float* y_tilde, const float* z_mean, const float* z_logvar,
+                int32_t step, const float* eps_z, float* stats_out, void* stream);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * sga_launch_count: kernels launched by this library in the calling thread since load.
