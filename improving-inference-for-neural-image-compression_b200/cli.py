@@ -14,7 +14,7 @@ import numpy as np
 SCRIPT_NAME = "sga"
 
 
-def parse_args(argv):
+def parse_args(argv, bb=False):
     try:
         from absl.flags import argparse_flags
         parser = argparse_flags.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
@@ -33,6 +33,9 @@ def parse_args(argv):
     c.add_argument("--sga_its", type=int, default=2000, help="Number of SGA iterations.")
     c.add_argument("--annealing_rate", type=float, default=1e-3, help="Annealing rate for SGA.")
     c.add_argument("--t0", type=int, default=700, help="Number of 'soft-quantization' iterations before annealing.")
+    if bb:
+        c.add_argument("--rate_its", type=int, default=2000,
+                       help="(new) iterations of the second, rate-only loop (bb_sga.py hard-codes r_opt_its = 2000).")
     c.add_argument("--operand", choices=["bf16", "f32"], default="bf16",
                    help="(new) arithmetic of the (de)conv stacks inside the loop; init and final eval are always f32.")
     c.add_argument("runname", help="Model name identifier, like 'mbt2018-num_filters=192-lmbda=0.01'")
@@ -129,7 +132,84 @@ def compress(args, out=print):
     return results
 
 
+def compress_bb(args, out=print):
+    """The `compress` command of the reference's bb_sga.py (bits-back variant): R-D loop over [y, z_mean, z_logvar]
+    (bb_sga.py:201-233), rate loop over [z_mean, z_logvar] with y_tilde = round(y) (:235-256), evaluation (:271-275),
+    output rd-bb_sga-lmbda=%g+<runname>-input=<file>.npz with the 8 fields of bb_sga.py:176."""
+    import torch
+    from . import dist as D
+    from . import weights as Wm
+    from .engine import BB_EVAL_FIELDS, BbEngine
+    from .msssim import msssim_per_image
+
+    rank, ws, local = D.init_process_group()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    say = out if rank == 0 else (lambda *a, **k: None)
+    X = load_input(args.input_file)
+    num_images, H, Wd = int(X.shape[0]), int(X.shape[1]), int(X.shape[2])
+    if args.lmbda < 0:                                        # bb_sga.py:150-152
+        args.lmbda = float(args.runname.split("lmbda=")[1].split("-")[0])
+        say("Defaulting lmbda (mse coefficient) to %g as used in model training." % args.lmbda)
+    W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, args.num_filters, bb=True)
+    results = {k: [] for k in BB_EVAL_FIELDS}
+    log_points = lambda its: [it for it in range(its) if it % 100 == 0 or it + 1 == its]
+    for (b_lo, b_hi) in D.reference_batches(num_images, H * Wd):
+        n_ref = b_hi - b_lo
+        lo, hi = D.shard_range(n_ref, rank, ws)
+        n_loc = hi - lo
+        rows = np.zeros((0, 8), dtype=np.float32)
+        say("----RD Optimization----")                        # bb_sga.py:202
+
+        def log(it, T, s):                                    # bb_sga.py:231-232
+            tot = D.allreduce_scalars([s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())])
+            say("it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (it, T, tot[0], tot[1], tot[2], tot[3] / n_ref))
+
+        def log_rate(it, s):                                  # bb_sga.py:254-255
+            if it == 0:
+                say()
+                say("----Rate Optimization----")
+            say("it=", it, "\trate=", D.allreduce_scalars([s["train_bpp"]])[0])
+
+        if n_loc > 0:
+            eng = BbEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref, operand=args.operand, seed=0,
+                           first_image=lo)
+            x = torch.from_numpy(X[b_lo + lo:b_lo + hi].astype(np.float32) / 255.0).cuda()
+            y_tilde, zm, zl, ev = eng.run(x, its=args.sga_its, r_its=args.rate_its, annealing_rate=args.annealing_rate,
+                                          t0=args.t0, log=log, log_rate=log_rate)
+            ms = msssim_per_image(eng.reconstruction(), x)
+            rows = np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
+                             ev["est_y_bpp"], ev["est_z_bpp"], ev["est_bpp_back"]], axis=1).astype(np.float32)
+            eng.close()
+        elif ws > 1:                                          # ranks without images still join the log all-reduces
+            for _ in log_points(args.sga_its):
+                D.allreduce_scalars([0.0] * 4)
+            for _ in log_points(args.rate_its):
+                D.allreduce_scalars([0.0])
+        say()
+        full = D.gather_rows(rows, n_ref, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
+        for i, k in enumerate(BB_EVAL_FIELDS):
+            results[k] += full[:, i].tolist()
+    if rank != 0:
+        return None
+    results = {k: np.asarray(v) for k, v in results.items()}
+    input_file = os.path.basename(args.input_file)
+    save_file = "rd-%s-input=%s.npz" % (args.runname, input_file)
+    if "bb_sga" != args.runname.split("-")[0]:                # bb_sga.py:283-287
+        save_file = "rd-%s-lmbda=%g+%s-input=%s.npz" % ("bb_sga", args.lmbda, args.runname, input_file)
+    np.savez(os.path.join(args.results_dir, save_file), **results)
+    for k in BB_EVAL_FIELDS:
+        say("Avg {}: {:0.4f}".format(k, results[k].mean()))   # bb_sga.py:290-292
+    return results
+
+
 def main(argv=None):
     args = parse_args(sys.argv if argv is None else argv)
     assert args.command == "compress", "Only compression is supported."     # sga.py:303
     compress(args)
+
+
+def main_bb(argv=None):
+    args = parse_args(sys.argv if argv is None else argv, bb=True)
+    assert args.command == "compress", "Only compression is supported."     # bb_sga.py:300
+    compress_bb(args)

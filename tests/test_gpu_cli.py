@@ -62,3 +62,29 @@ def test_compress_cli_two_ranks_match_one(tmp_path):
     # gradient scale is 1/n_ref on every shard: the per-image results do not depend on the sharding
     assert np.abs(res[0]["est_bpp"] - res[1]["est_bpp"]).max() < 1e-4 * res[0]["est_bpp"].max()
     assert np.abs(res[0]["psnr"] - res[1]["psnr"]).max() < 1e-3
+
+
+def test_compress_cli_bits_back(tmp_path):
+    """bb_sga.py compress: both loops, the 8 result fields of bb_sga.py:176, reference file naming."""
+    import sga_b200
+    rn = sga_b200.weights.runname(64, 0.01, prefix="mbt2018_bb")
+    sga_b200.weights.save_checkpoint(str(tmp_path / "ckpt"), rn, sga_b200.weights.make_synthetic_bb(64, 0))
+    inp = tmp_path / "imgs.npy"
+    np.save(inp, sga_b200.synth.synthetic_images(2, 64, 96, 1))
+    (tmp_path / "res").mkdir()
+    cmd = [sys.executable, os.path.join(ROOT, "bb_sga.py"), "--num_filters", "64", "--checkpoint_dir", str(tmp_path / "ckpt"),
+           "compress", "--sga_its", "12", "--rate_its", "8", "--results_dir", str(tmp_path / "res"), rn, str(inp)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    assert "----RD Optimization----" in out and "it=0, T=0.500 rd_loss=" in out and "it=11, T=0.500" in out
+    assert "----Rate Optimization----" in out and "it= 7" in out and "rate=" in out
+    assert "Avg est_bpp_back:" in out
+    f = tmp_path / "res" / ("rd-bb_sga-lmbda=0.01+%s-input=imgs.npy.npz" % rn)                   # bb_sga.py:283-287
+    assert f.exists(), os.listdir(tmp_path / "res")
+    d = np.load(f)
+    assert sorted(d.files) == sorted(["mse", "psnr", "msssim", "msssim_db", "est_bpp", "est_y_bpp", "est_z_bpp",
+                                      "est_bpp_back"])
+    assert all(d[k].shape == (2,) for k in d.files)
+    assert np.allclose(d["est_bpp"], d["est_y_bpp"] + d["est_z_bpp"] - d["est_bpp_back"], rtol=1e-4, atol=1e-5)
+    assert np.isfinite(d["psnr"]).all()

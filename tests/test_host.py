@@ -98,6 +98,22 @@ def test_cli_surface_matches_reference():
     assert a.verbose and a.lmbda == 0.08 and a.sga_its == 10 and a.t0 == 350 and a.output_file == "o"
     with pytest.raises(SystemExit):
         parse_args(["sga.py"])
+    b = parse_args(["bb_sga.py", "--num_filters", "192", "compress", "mbt2018_bb-num_filters=192-lmbda=0.01", "in.npy"], bb=True)
+    assert b.sga_its == 2000 and b.rate_its == 2000 and b.lmbda == -1          # bb_sga.py:186-192
+
+
+def test_bits_back_weights_layout(tmp_path):
+    """bb_sga.py:63-70: 2C-channel h_a output, BMSHJ2018Prior variables instead of the EntropyBottleneck's."""
+    from sga_b200 import weights as Wm
+    W = Wm.make_synthetic_bb(8, 0)
+    assert W["hyper_analysis_transform/layer_2/kernel"].shape == (5, 5, 8, 16)
+    assert "bmsh_j2018prior/matrix_0" in W and not any(k.startswith("entropy_bottleneck/") for k in W)
+    rn = Wm.runname(8, 0.01, prefix="mbt2018_bb")
+    Wm.save_checkpoint(str(tmp_path), rn, W)
+    W2 = Wm.load_checkpoint(str(tmp_path), rn, 8, bb=True)
+    assert set(W2) == set(W) and all(np.array_equal(W2[k], W[k]) for k in W)
+    with pytest.raises(KeyError):
+        Wm.load_checkpoint(str(tmp_path), rn, 8)          # not a mean-scale (sga.py) checkpoint
 
 
 def test_batch_segmentation_and_shards():
