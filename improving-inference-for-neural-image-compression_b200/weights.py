@@ -2,8 +2,9 @@
 
 The reference restores a TF1 checkpoint from ``<checkpoint_dir>/<runname>/`` (sga.py:180-182,
 tf_boilerplate.py:47-48) whose variables are created by the Keras layers in nn_models.py.  This
-module keeps that directory layout and those variable names; the container is ``model.npz``
-(one array per variable) because TensorFlow is not available to write/read V2 bundles here.
+module keeps that directory layout and those variable names; it reads either the reference's own
+TF V2 bundle (``checkpoint`` + ``<prefix>.index`` / ``.data-*``, parsed by tf_bundle.py without
+TensorFlow) or a ``model.npz`` container (one array per variable).
 
 Variable names (Keras TF1 scopes):
   analysis_transform/layer_{0..3}/{kernel|kernel_rdft, bias}, layer_{0..2}/gdn_{i}/{beta|reparam_beta, gamma|reparam_gamma}
@@ -188,8 +189,9 @@ def irdft_matrix(shape):
     return np.stack(basis, axis=1)
 
 
-def deparameterise(raw):
-    """Convert any `kernel_rdft` / `reparam_beta` / `reparam_gamma` entries to plain variables."""
+def deparameterise(raw, shapes=None):
+    """Convert any `kernel_rdft` / `reparam_beta` / `reparam_gamma` entries to plain variables.  `shapes` (name -> shape of
+    the plain variables) supplies the kernel support when no `kernel_shape` sibling is stored (TF bundles)."""
     W = {}
     for name, arr in raw.items():
         arr = np.asarray(arr)
@@ -200,6 +202,8 @@ def deparameterise(raw):
             W[head + "/gamma"] = gdn_from_reparam(arr, GDN_GAMMA_MIN)
         elif leaf == "kernel_rdft":
             shp = raw[head + "/kernel_shape"] if head + "/kernel_shape" in raw else None
+            if shp is None and shapes is not None:
+                shp = shapes.get(head + "/kernel")
             if shp is None:
                 raise ValueError("kernel_rdft needs a sibling kernel_shape entry: %s" % name)
             kh, kw, ci, co = (int(v) for v in shp)
@@ -235,13 +239,21 @@ def load_checkpoint(checkpoint_dir, runname, num_filters, bb=False):
     """Mirror of tf.train.latest_checkpoint + Saver.restore (sga.py:180-182)."""
     d = os.path.join(checkpoint_dir, runname)
     path = os.path.join(d, "model.npz")
-    if not os.path.exists(path):
-        raise FileNotFoundError(
-            "no model.npz under %s (TF V2 bundles are not readable without TensorFlow; "
-            "export the variables to model.npz with the names listed in weights.py)" % d)
-    with np.load(path) as f:
-        raw = {k: f[k] for k in f.files}
-    W = deparameterise(raw)
+    want = variable_shapes_bb(num_filters) if bb else variable_shapes(num_filters)
+    if os.path.exists(path):
+        with np.load(path) as f:
+            raw = {k: f[k] for k in f.files}
+    else:
+        # the reference's own format: a TF V2 bundle named by the `checkpoint` state file (tf_bundle.py)
+        from . import tf_bundle
+        prefix = tf_bundle.latest_checkpoint(d)
+        if prefix is None or not os.path.exists(prefix + ".index"):
+            raise FileNotFoundError("no model.npz and no TensorFlow checkpoint (checkpoint + <prefix>.index/.data-*) under %s" % d)
+        heads = {k.rsplit("/", 1)[0] for k in want}
+        raw = tf_bundle.read_bundle(prefix, names=lambda n: n.rsplit("/", 1)[0] in heads and
+                                    n.rsplit("/", 1)[-1] in ("kernel", "kernel_rdft", "bias", "beta", "gamma", "reparam_beta",
+                                                             "reparam_gamma") or n in want)
+    W = deparameterise(raw, shapes=want)
     check_complete(W, num_filters, bb=bb)
     return W
 

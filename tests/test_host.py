@@ -158,3 +158,46 @@ def test_gather_results_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_tf_bundle_roundtrip_and_checkpoint_loading(tmp_path):
+    """sga.py:180-182: <checkpoint_dir>/<runname>/{checkpoint, <prefix>.index, <prefix>.data-00000-of-00001}.  The
+    writer/reader pair restates the TF V2 bundle format (tf_bundle.py); re-parameterised variables and optimizer slots
+    as a TF1 Saver would store them are handled on load."""
+    from sga_b200 import tf_bundle, weights as Wm
+    assert tf_bundle.crc32c(b"123456789") == 0xE3069283                      # CRC-32C check value
+    C = 8
+    W = Wm.make_synthetic(C, 0)
+    rn = Wm.runname(C, 0.01)
+    d = tmp_path / rn
+    d.mkdir()
+    stored = {}
+    for k, v in W.items():
+        leaf = k.rsplit("/", 1)[-1]
+        if leaf == "beta":
+            stored[k.replace("/beta", "/reparam_beta")] = Wm.gdn_to_reparam(v, Wm.GDN_BETA_MIN)
+        elif leaf == "gamma":
+            stored[k.replace("/gamma", "/reparam_gamma")] = Wm.gdn_to_reparam(v, Wm.GDN_GAMMA_MIN)
+        elif leaf == "kernel" and not k.startswith("mb_t2018hyper_synthesis_transform"):
+            kh, kw, ci, co = v.shape                                          # default RDFT parameterisation (nn_models.py)
+            M = Wm.irdft_matrix((kh, kw))
+            stored[k + "_rdft"] = (M.T @ v.reshape(kh * kw, ci * co).astype(np.float64)).astype(np.float32)
+        else:
+            stored[k] = v
+    stored["global_step"] = np.asarray(1000000, dtype=np.int64)
+    stored["analysis_transform/layer_0/bias/Adam"] = np.zeros(C, np.float32)  # optimizer slot: ignored
+    prefix = str(d / "model.ckpt-1000000")
+    tf_bundle.write_bundle(prefix, stored, restart_interval=4, block_entries=7)   # several blocks, shared key prefixes
+    assert tf_bundle.latest_checkpoint(str(d)) == prefix
+    back = tf_bundle.read_bundle(prefix, verify=True)
+    assert set(back) == set(stored)
+    assert all(np.array_equal(back[k], stored[k]) and back[k].dtype == stored[k].dtype for k in stored)
+    W2 = Wm.load_checkpoint(str(tmp_path), rn, C)
+    assert set(W2) == set(W)
+    for k in W:
+        assert np.allclose(W2[k], W[k], rtol=1e-5, atol=1e-6), k
+    bad = bytearray(open(prefix + ".index", "rb").read())
+    bad[10] ^= 0xFF
+    open(prefix + ".index", "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        tf_bundle.read_index(prefix + ".index")
