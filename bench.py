@@ -284,6 +284,8 @@ def main_ours(args, rank, ws, local):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     last = eng.unpack_stats(stats_host[args.warmup + args.steps - 1].numpy())
+    if not (np.isfinite(stats_host.numpy()).all()):
+        raise RuntimeError("non-finite SGA statistics inside the timed loop (rd_loss %r): the measurement is void" % last["rd_loss"])
 
     if rank != 0:
         return

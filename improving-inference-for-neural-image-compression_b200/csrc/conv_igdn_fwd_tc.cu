@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
       tcgen05_fence_before();
       __syncwarp();
       if (it == 0) mbar_wait(bar_g, 0);    // this CTA's gamma rows are resident before the leader may issue the mixing
-      if (lane == 0) arrive_lead(bar_a2full, lead_a2full);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster_release(lead_a2full); else mbar_arrive(bar_a2full);
+      }
       ++it;
     }
     if (dbg_print && warp == 2)

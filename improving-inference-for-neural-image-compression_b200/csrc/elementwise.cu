@@ -49,8 +49,12 @@ __device__ __forceinline__ float soft_round_fast(float v, float u0, float u1, fl
   const float dc = fminf(d, hi), ec = fminf(e, hi);
   const float invT = __frcp_rn(T);
   const float ld = __logf(__fdividef((1.0f + dc) * (1.0f - ec), (1.0f - dc) * (1.0f + ec)));
-  // log(u) keeps the accurate logf: u reaches 1 - 2^-25, where the SFU logarithm's absolute error exceeds the value
-  const float lg = __logf(__fdividef(logf(u0), logf(u1)));
+  // -log(u) keeps the accurate logf: near u = 1 the SFU logarithm's absolute error exceeds the value.  The uniform
+  // ((bits >> 8) + 0.5) * 2^-24 rounds to exactly 1.0f once in 2^24 draws (about once per iteration at the headline
+  // shape): the reference form then has G = -log(-log 1) = +inf and a hard 0/1 sample; the floor keeps the ratio finite
+  // and saturates the sigmoid the same way.
+  const float n0 = fmaxf(-logf(u0), 1e-37f), n1 = fmaxf(-logf(u1), 1e-37f);
+  const float lg = __logf(__fdividef(n0, n1));
   const float a = (0.5f * invT * ld + lg) * invT;
   const float s1 = __frcp_rn(1.0f + __expf(-a));
   const float s0 = 1.0f - s1;

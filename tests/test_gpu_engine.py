@@ -122,3 +122,39 @@ def test_loop_bf16_matches_f32_loop():
         res[operand] = ev
     assert np.abs(res["bf16"]["est_bpp"] - res["f32"]["est_bpp"]).max() < 5e-3 * res["f32"]["est_bpp"].max()
     assert np.abs(res["bf16"]["psnr"] - res["f32"]["psnr"]).max() < 0.05
+
+
+def test_uniform_equal_to_one_is_harmless():
+    """((bits >> 8) + 0.5) * 2^-24 rounds to exactly 1.0f once in 2^24 draws: G = -log(-log 1) = +inf, a hard 0/1 sample.
+    Both arithmetic paths must stay finite and agree with the oracle there (a NaN would poison y through Adam)."""
+    C, n, h, w = 64, 1, 64, 64
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=2)
+    g = torch.Generator().manual_seed(9)
+    uy = torch.rand((2,) + tuple(y.shape), generator=g).clamp(1e-6, 1 - 1e-6)
+    uz = torch.rand((2,) + tuple(z.shape), generator=g).clamp(1e-6, 1 - 1e-6)
+    uy[0].view(-1)[::7] = 1.0          # DOWN logit noise = +inf
+    uy[1].view(-1)[3::11] = 1.0        # UP logit noise = +inf (never both: 7 and 11k+3 coincide only at multiples of 77 + 14 ...)
+    both = (uy[0] == 1.0) & (uy[1] == 1.0)
+    uy[1][both] = 0.5
+    uz[1].view(-1)[::5] = 1.0
+    ref = O.sga_graph(x, y, z, Wt, 0.4, (uy[0], uy[1], uz[0], uz[1]), 0.01)
+    assert torch.isfinite(ref["grad_y"]).all()
+    for operand, tol in (("f32", 2e-4), ("bf16", 3e-2)):
+        eng = _engine(W, n, h, w, C, 0.01, operand)
+        gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.4, 0, uy.contiguous().cuda(), uz.contiguous().cuda())
+        assert torch.isfinite(gy).all() and torch.isfinite(gz).all() and np.isfinite(stats.cpu().numpy()).all()
+        err = rms_rel_err(gy, ref["grad_y"]) if operand == "bf16" else rel_err(gy, ref["grad_y"])
+        assert err < tol, (operand, err)
+
+
+def test_long_bf16_loop_stays_finite_and_descends():
+    """300 SGA steps with the Philox stream (u = 1.0f does occur at this length): finite state, lower R-D loss."""
+    C, n, h, w = 64, 2, 256, 256
+    W, Wt, x, _, _ = make_case(C, n, h, w, seed=6)
+    eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=5)
+    losses = []
+    y, z, ev = eng.run(x.cuda(), its=300, annealing_rate=5e-3, t0=100, log_itv=50,
+                       log=lambda it, T, s, extra: losses.append(s["rd_loss"]))
+    assert torch.isfinite(y).all() and torch.isfinite(z).all()
+    assert all(np.isfinite(l) for l in losses) and losses[-1] < losses[0]
+    assert np.isfinite(ev["psnr"]).all() and np.isfinite(ev["est_bpp"]).all()
