@@ -34,7 +34,7 @@ struct alignas(64) TcParams {
   int n_sp;               // spatial tiles per job and N tile = N * tiles_h * tiles_w
   int n_sp_pairs;         // CTA-pair mode: ceil(n_sp / 2)
   int relu;
-  int dbg;                // debug/timing experiments only (env SGA_DBG): 1 skip xpre store, 2 skip s store, 4 skip out store
+  int dbg;                // development aid (env SGA_DBG): bit 3 = per-role wait-cycle accounting printed by two CTAs
   int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
   long long oN;
   const float* bias;
