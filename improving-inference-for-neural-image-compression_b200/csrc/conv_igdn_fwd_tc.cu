@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
   constexpr int kGTile = (64 / CG) * 128;           // gamma rows of one part held by this CTA x one K chunk
   constexpr int kGBytes = NP * KC * kGTile;
   constexpr int kA2Bytes = KC * kABytes;
+  pdl_launch_dependents();
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
   tcgen05_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
+  pdl_grid_dependency_wait();        // everything above touches only constants (bias, beta) and on-chip state
   const uint32_t tmem_base = *s_tmem;
   const int nwaves = num_waves<CG>(P);
   auto arrive_lead = [](uint32_t local_bar, uint32_t lead_bar) {
@@ -369,13 +371,15 @@ int launch_igdn_fwd_kernel(const TcConv* c, const TcParams& P, cudaStream_t st) 
   cfg.blockDim = dim3(kFwdThreads, 1, 1);
   cfg.dynamicSmemBytes = static_cast<size_t>(c->smem_bytes);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(c->cg);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   SGA_CUDA(cudaLaunchKernelEx(&cfg, select_fwd(P.Nn, c->cg), P));
   g_launches += 1;
   return SGA_OK;

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   static_assert(FUSE == 0 || G * 64 == NF, "fused variants: one 32-column chunk per warp and half");
   static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
   static_assert(FUSE == 0 || FUSE == 2, "the forward fusion lives in conv_igdn_fwd_tc.cu");
+  pdl_launch_dependents();
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
   extern __shared__ uint8_t smem_raw[];
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   tcgen05_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
+  pdl_grid_dependency_wait();        // everything above touches only constants (bias) and on-chip state
   const uint32_t tmem_base = *s_tmem;
   const int nwaves = num_waves<CG>(P);
   // wait on a barrier the peer CTA arrives on / arrive on a leader barrier
@@ -500,6 +502,11 @@ static TcKernel select_kernel(int fuse, int nf, int cg) {
 }
 static int kernel_threads(int fuse, int nf) { return 64 + 128 * (fuse == 0 ? kPlainGroups : nf / 64); }
 
+bool pdl_enabled() {
+  static const bool on = getenv("SGA_NO_PDL") == nullptr;
+  return on;
+}
+
 // one launch path for both modes: CTA pairs need the cluster dimension attribute
 static int launch_tc(const TcConv* c, const TcParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
@@ -508,13 +515,15 @@ static int launch_tc(const TcConv* c, const TcParams& P, cudaStream_t st) {
   cfg.blockDim = dim3(static_cast<unsigned>(kernel_threads(c->fuse, P.Nn)), 1, 1);
   cfg.dynamicSmemBytes = static_cast<size_t>(c->smem_bytes);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(c->cg);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_* in tc_common.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   SGA_CUDA(cudaLaunchKernelEx(&cfg, select_kernel(c->fuse, P.Nn, c->cg), P));
   g_launches += 1;
   return SGA_OK;

@@ -108,6 +108,8 @@ struct TcConv {
   ConvPlan plan;
 };
 
+bool pdl_enabled();   // programmatic dependent launch between the kernels of a step (env SGA_NO_PDL disables)
+
 // conv_igdn_fwd_tc.cu: the forward (de)conv fused with the inverse GDN (fuse == 1)
 int igdn_fwd_smem_fixed(int cout, int cg);          // shared memory outside the operand ring
 int igdn_fwd_set_attr(int cout, int cg);

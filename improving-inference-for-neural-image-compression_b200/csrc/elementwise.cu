@@ -14,8 +14,35 @@
 #include "philox.cuh"
 #include "kernels.h"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace sga {
+
+// Programmatic dependent launch (see tc_common.cuh): the loop's elementwise kernels let the tensor kernel behind them
+// start its prologue early, and wait for the kernel in front of them before touching memory.
+__device__ __forceinline__ void ew_pdl_begin() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();   // conv_tc.cu
+
+template <typename... KArgs, typename... Args>
+static int launch_ew(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool ew_pdl = pdl_enabled() && getenv("SGA_NO_EW_PDL") == nullptr;
+  cfg.numAttrs = ew_pdl ? 1 : 0;
+  SGA_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  ++g_launches;
+  return SGA_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // soft round of one element. Returns v_tilde, writes d v_tilde / d v.
@@ -218,6 +245,7 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
                          long long per_image, int C, const float* __restrict__ pk, float T, float eps, uint64_t seed,
                          int step, int hard, float rate_scale, AT* __restrict__ zt_act, float* __restrict__ g_rate,
                          float* __restrict__ dz, double* __restrict__ bits, long long ctr_off) {
+  ew_pdl_begin();
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long e0 = pair * 2;
   float nll = 0.0f;
@@ -311,6 +339,7 @@ __global__ void k_zbb_path(const float* __restrict__ z_mean, const float* __rest
                            const float* __restrict__ pk, uint64_t seed, int step, float rate_scale, AT* __restrict__ zt_act,
                            float* __restrict__ g_zt, float* __restrict__ dzl, double* __restrict__ bits,
                            double* __restrict__ logq, long long ctr_off) {
+  ew_pdl_begin();
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long e0 = pair * 2;
   float nll = 0.0f, lq = 0.0f;
@@ -365,6 +394,7 @@ __global__ void k_zbb_path(const float* __restrict__ z_mean, const float* __rest
 // the loss with +rate_scale: eval_bpp = ... - bpp_back, bpp_back = -sum log q / (ln2 HW))
 __global__ void k_bb_grads(const float* __restrict__ g_rate, const float* __restrict__ g_hyper, const float* __restrict__ dzl,
                            long long numel, float half_scale, float* __restrict__ g_mean, float* __restrict__ g_lv) {
+  ew_pdl_begin();
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (e >= numel) return;
   const float g = g_rate[e] + g_hyper[e];
@@ -386,6 +416,7 @@ __global__ void k_split2(const float* __restrict__ in, long long pixels, int C, 
 // bits-back statistics: rd_loss, train_mse, train_bpp, then per image psnr, y_bpp, z_bpp, sse, mse_rounded, bpp_back
 __global__ void k_finalize_stats_bb(const double* __restrict__ acc, int N, int n_ref, int H, int W, float lmbda,
                                     int rate_only, float* __restrict__ out) {
+  ew_pdl_begin();
   // acc: [0,N) y nats, [N,2N) z nats, [2N,3N) sse, [3N,4N) sse rounded, [4N,5N) sum log q
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double npix = static_cast<double>(H) * W;
@@ -474,6 +505,7 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
                          int N, int Hy, int Wy, int Hh, int Wh, int C, float T, float eps, uint64_t seed, int step,
                          int hard, float rate_scale, AT* __restrict__ yt_act, float* __restrict__ g_rate,
                          float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits, long long ctr_off) {
+  ew_pdl_begin();
   const int halfC = C >> 1;
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long npairs = static_cast<long long>(N) * Hh * Wh * halfC;
@@ -592,6 +624,7 @@ __global__ void k_distortion(const float* __restrict__ x, const float* __restric
 // stats_out (sga_b200.h): rd_loss, train_mse, train_bpp, then per image psnr, y_bpp, z_bpp, sse, mse_rounded
 __global__ void k_finalize_stats(const double* __restrict__ acc, int N, int n_ref, int H, int W, float lmbda,
                                  float* __restrict__ out) {
+  ew_pdl_begin();
   // acc: [0,N) y nats, [N,2N) z nats, [2N,3N) sse, [3N,4N) sse rounded
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double npix = static_cast<double>(H) * W;
@@ -622,6 +655,7 @@ __global__ void k_finalize_stats(const double* __restrict__ acc, int N, int n_re
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
                        const float* __restrict__ gb, const float* __restrict__ fac, long long numel, float lr_t,
                        float b1, float omb1, float b2, float omb2, float eps, float* __restrict__ g_out) {
+  ew_pdl_begin();
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (e >= numel) return;
   float g = ga[e];
@@ -651,6 +685,7 @@ __device__ __forceinline__ float adam_one(float g, float& p, float& m, float& v,
 __global__ void k_adam_v4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
                           const float* __restrict__ gb, const float* __restrict__ fac, long long numel4, float lr_t, float b1,
                           float omb1, float b2, float omb2, float eps) {
+  ew_pdl_begin();
   const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (q >= numel4) return;
   float4 g4 = reinterpret_cast<const float4*>(ga)[q];
@@ -747,10 +782,8 @@ int launch_z_path(const float* z, const float* inj, long long numel, long long p
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
                   float* dz, double* bits, long long ctr_off, cudaStream_t st) {
   const long long pairs = (numel + 1) / 2;
-  k_z_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(z, inj, numel, per_image, C, pk, T, eps, seed, step, hard,
-                                                       rate_scale, zt_act, g_rate, dz, bits, ctr_off);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_z_path<AT>, blocks_for(pairs, 256), 256, st, z, inj, numel, per_image, C, pk, T, eps, seed, step, hard,
+                   rate_scale, zt_act, g_rate, dz, bits, ctr_off);
 }
 template int launch_z_path<float>(const float*, const float*, long long, long long, int, const float*, float, float,
                                   uint64_t, int, int, float, float*, float*, float*, double*, long long, cudaStream_t);
@@ -763,10 +796,8 @@ int launch_y_path(const float* y, const float* inj, const float* h2, int N, int 
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
                   float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st) {
   const long long pairs = static_cast<long long>(N) * Hh * Wh * (C / 2);
-  k_y_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step, hard,
-                                                       rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_y_path<AT>, blocks_for(pairs, 256), 256, st, y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step, hard,
+                   rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off);
 }
 template int launch_y_path<float>(const float*, const float*, const float*, int, int, int, int, int, int, float, float,
                                   uint64_t, int, int, float, float*, float*, float*, float*, double*, long long, cudaStream_t);
@@ -787,10 +818,8 @@ int launch_zbb_path(const float* z_mean, const float* z_logvar, const float* eps
                     int C, const float* pk, uint64_t seed, int step, float rate_scale, AT* zt_act, float* g_zt, float* dzl,
                     double* bits, double* logq, long long ctr_off, cudaStream_t st) {
   const long long pairs = (numel + 1) / 2;
-  k_zbb_path<AT><<<blocks_for(pairs, 256), 256, 0, st>>>(z_mean, z_logvar, eps_inj, numel, per_image, C, pk, seed, step,
-                                                         rate_scale, zt_act, g_zt, dzl, bits, logq, ctr_off);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_zbb_path<AT>, blocks_for(pairs, 256), 256, st, z_mean, z_logvar, eps_inj, numel, per_image, C, pk, seed, step,
+                   rate_scale, zt_act, g_zt, dzl, bits, logq, ctr_off);
 }
 template int launch_zbb_path<float>(const float*, const float*, const float*, long long, long long, int, const float*,
                                     uint64_t, int, float, float*, float*, float*, double*, double*, long long, cudaStream_t);
@@ -801,9 +830,7 @@ template int launch_zbb_path<__nv_bfloat16>(const float*, const float*, const fl
 int launch_bb_grads(const float* g_rate, const float* g_hyper, const float* dzl, long long numel, float half_scale,
                     float* g_mean, float* g_lv, cudaStream_t st) {
   if (numel <= 0) return SGA_OK;
-  k_bb_grads<<<blocks_for(numel, 256), 256, 0, st>>>(g_rate, g_hyper, dzl, numel, half_scale, g_mean, g_lv);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_bb_grads, blocks_for(numel, 256), 256, st, g_rate, g_hyper, dzl, numel, half_scale, g_mean, g_lv);
 }
 
 int launch_split2(const float* in, long long pixels, int C, float* a, float* b, cudaStream_t st) {
@@ -815,15 +842,11 @@ int launch_split2(const float* in, long long pixels, int C, float* a, float* b, 
 
 int launch_finalize_stats_bb(const double* acc, int N, int n_ref, int H, int W, float lmbda, int rate_only, float* out,
                              cudaStream_t st) {
-  k_finalize_stats_bb<<<1, 32, 0, st>>>(acc, N, n_ref, H, W, lmbda, rate_only, out);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_finalize_stats_bb, 1, 32, st, acc, N, n_ref, H, W, lmbda, rate_only, out);
 }
 
 int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st) {
-  k_finalize_stats<<<1, 32, 0, st>>>(acc, N, n_ref, H, W, lmbda, out);
-  SGA_LAUNCH_CHECK();
-  return SGA_OK;
+  return launch_ew(k_finalize_stats, 1, 32, st, acc, N, n_ref, H, W, lmbda, out);
 }
 
 int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, const float* fac, long long numel,
@@ -837,16 +860,13 @@ int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, 
   long long done = 0;
   if (p != nullptr && g_out == nullptr && numel >= 4 && al16(p) && al16(m) && al16(v) && al16(ga) && al16(gb) && al16(fac)) {
     const long long n4 = numel / 4;
-    k_adam_v4<<<blocks_for(n4, 256), 256, 0, st>>>(p, m, v, ga, gb, fac, n4, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps);
-    SGA_LAUNCH_CHECK();
+    SGA_TRY(launch_ew(k_adam_v4, blocks_for(n4, 256), 256, st, p, m, v, ga, gb, fac, n4, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps));
     done = n4 * 4;
   }
   if (done < numel) {   // tail (or everything: unaligned buffers, gradient-only calls)
-    k_adam<<<blocks_for(numel - done, 256), 256, 0, st>>>(p ? p + done : nullptr, m ? m + done : nullptr, v ? v + done : nullptr,
-                                                          ga + done, gb ? gb + done : nullptr, fac ? fac + done : nullptr,
-                                                          numel - done, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps,
-                                                          g_out ? g_out + done : nullptr);
-    SGA_LAUNCH_CHECK();
+    SGA_TRY(launch_ew(k_adam, blocks_for(numel - done, 256), 256, st, p ? p + done : nullptr, m ? m + done : nullptr,
+                      v ? v + done : nullptr, ga + done, gb ? gb + done : nullptr, fac ? fac + done : nullptr, numel - done,
+                      f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps, g_out ? g_out + done : nullptr));
   }
   return SGA_OK;
 }

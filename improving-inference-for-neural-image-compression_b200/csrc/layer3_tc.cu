@@ -12,6 +12,7 @@
 //     the gradient patch, directly in the no-swizzle K-major core-matrix layout the tensor core reads.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "conv_tc.cuh"
 
 namespace sga {
 
@@ -41,6 +42,7 @@ struct alignas(64) L3FwdParams {
 };
 
 __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant__ L3FwdParams P) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_grid_dependency_wait();
   const uint32_t tmem_base = *s_tmem;
   const int tiles_per_img = P.tiles_h * P.tiles_w;
 
@@ -461,6 +464,7 @@ __device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, i
 
 template <int NF>
 __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
+  pdl_launch_dependents();
   constexpr int G = NF / 64;                 // worker groups (column split)
   constexpr int kWorkers = 128 * G;
   constexpr int kKc = NF / 64;               // K chunks of the mixing GEMM
@@ -524,6 +528,7 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_grid_dependency_wait();        // above: gather weights (constants) and on-chip state only
   const uint32_t tmem_base = *s_tmem;
   const int tiles_per_img = P.tiles_h * P.tiles_w;
   const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
@@ -731,6 +736,24 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
 // =====================================================================================================
 // host
 // =====================================================================================================
+template <typename Params>
+static int launch_pdl(void (*kernel)(const Params), int grid, int threads, int smem, cudaStream_t st, const Params& P) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(threads), 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SGA_CUDA(cudaLaunchKernelEx(&cfg, kernel, P));
+  g_launches += 1;
+  return SGA_OK;
+}
+
 struct L3Tc {
   L3FwdParams F;
   L3DgradParams D;
@@ -849,8 +872,7 @@ int l3_tc_forward(const L3Tc* c, const float* bias_dev_host3, const float* x, fl
   L3FwdParams F = c->F;
   F.bias[0] = bias_dev_host3[0]; F.bias[1] = bias_dev_host3[1]; F.bias[2] = bias_dev_host3[2];
   F.x = x; F.grad_scale = grad_scale; F.xt_out = xt_out; F.gx = gx; F.sse = sse; F.sse_r = sse_r;
-  k_l3_fwd<<<c->f_grid, kL3Threads, c->f_smem, st>>>(F);
-  SGA_LAUNCH_CHECK();
+  SGA_TRY(launch_pdl(k_l3_fwd, c->f_grid, kL3Threads, c->f_smem, st, F));
   return SGA_OK;
 }
 
@@ -872,10 +894,9 @@ int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out,
   L3DgradFusedParams D = c->DF;
   D.gx = gx; D.out = out;
   const int threads = 64 + 128 * (C / 64);
-  if (C == 192) k_l3_dgrad_igdn<192><<<c->d_grid, threads, c->df_smem, st>>>(D);
-  else if (C == 128) k_l3_dgrad_igdn<128><<<c->d_grid, threads, c->df_smem, st>>>(D);
-  else k_l3_dgrad_igdn<64><<<c->d_grid, threads, c->df_smem, st>>>(D);
-  SGA_LAUNCH_CHECK();
+  if (C == 192) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
+  else if (C == 128) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<128>, c->d_grid, threads, c->df_smem, st, D));
+  else SGA_TRY(launch_pdl(k_l3_dgrad_igdn<64>, c->d_grid, threads, c->df_smem, st, D));
   return SGA_OK;
 }
 

@@ -120,6 +120,14 @@ __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_add
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// ---------------- programmatic dependent launch ----------------
+// Kernels of one step are launched back to back on one stream.  launch_dependents (first instruction) lets the next
+// kernel's CTAs become resident -- on SMs this kernel does not occupy -- and run their prologue (barrier init, TMEM
+// allocation, descriptor prefetch) early; grid_dependency_wait returns once every kernel this one depends on has
+// completed and flushed its memory.  Nothing produced by an earlier kernel may be touched before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------- proxies / fences ----------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
