@@ -269,9 +269,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
       tcgen05_fence_before();
       __syncwarp();
       if (it == 0) mbar_wait(bar_g, 0);    // this CTA's gamma rows are resident before the leader may issue the mixing
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster_release(lead_a2full); else mbar_arrive(bar_a2full);
-      }
+      // default (.release.cta) arrive as everywhere else: the operand sits in THIS CTA's shared memory and was made
+      // visible to the async proxy by the fence above; CUTLASS signals its 2-SM mainloops the same way.  (A
+      // .release.cluster arrive costs a MEMBAR.ALL.CTA per warp and tile: +3 % kernel time.)
+      if (lane == 0) arrive_lead(bar_a2full, lead_a2full);
       ++it;
     }
     if (dbg_print && warp == 2)

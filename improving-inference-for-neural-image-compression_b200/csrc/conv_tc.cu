@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster_release(lead_a2); else mbar_arrive(bar_a2);
+          arrive_lead(bar_a2, lead_a2);
           arrive_lead(bar_tempty + 8 * buf, lead_tempty + 8 * buf);
         }
         // ---------- pass 2: two halves of the mixing result; this warp owns chunk `grp` of each half

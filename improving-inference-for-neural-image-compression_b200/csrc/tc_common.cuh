@@ -114,12 +114,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-// same with release at cluster scope: for the one arrive per warp and tile that PUBLISHES data (the mixing operand the
-// peer wrote to its shared memory) to the leader's MMA warp
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-
 // ---------------- programmatic dependent launch ----------------
 // Kernels of one step are launched back to back on one stream.  launch_dependents (first instruction) lets the next
 // kernel's CTAs become resident -- on SMs this kernel does not occupy -- and run their prologue (barrier init, TMEM
