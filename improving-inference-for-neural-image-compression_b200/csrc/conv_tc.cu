@@ -546,8 +546,6 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   c->plan = plan;
   TcParams& P = c->P;
   P.N = g.N; P.K = g.Cin; P.Nn = g.Cout;
-  P.block_n = pick_block_n(g.Cout);
-  P.n_tiles_n = g.Cout / P.block_n;
   P.kchunks = ceil_div(g.Cin, kBlockK);
   P.njobs = plan.njobs;
   {
@@ -565,7 +563,24 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.tiles_w = ceil_div(plan.job[0].Wo, P.TW);
   P.n_sp = g.N * P.tiles_h * P.tiles_w;
   P.n_sp_pairs = (P.n_sp + 1) / 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = (c->cg == 2) ? sms / 2 : sms;                 // CTAs (or CTA pairs) that can be resident
+  const int sp_units = (c->cg == 2) ? P.n_sp_pairs : P.n_sp;
+  // N tile: the whole of Cout when it fits an MMA; small problems of the un-fused kernel take narrower tiles (down to
+  // 64) until at least half of the CTAs have a unit -- they are latency bound, not tensor bound
+  P.block_n = pick_block_n(g.Cout);
+  if (fuse == 0 && getenv("SGA_NO_SMALL") == nullptr) {
+    for (int bn = P.block_n; bn >= 64; bn -= 16) {
+      if (g.Cout % bn != 0 || (bn / c->cg) % 8 != 0) continue;
+      P.block_n = bn;
+      if (sp_units * (g.Cout / bn) * plan.njobs * 2 >= ctas) break;
+    }
+  }
+  P.n_tiles_n = g.Cout / P.block_n;
   P.n_spatial = P.n_sp * P.n_tiles_n;
+  P.spread = (sp_units * P.n_tiles_n < ctas && getenv("SGA_NO_SMALL") == nullptr) ? 1 : 0;
   const int b_bytes = (P.block_n / c->cg) * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
   const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + 512 * 4 + 256;
@@ -620,14 +635,9 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (c->cg == 2) {
-    const int units = P.n_sp_pairs * P.n_tiles_n, pairs = sms / 2;
-    c->grid = 2 * (units < pairs ? units : pairs);
-  } else {
-    c->grid = (P.n_spatial < sms) ? P.n_spatial : sms;
+  {
+    const int units = sp_units * P.n_tiles_n * (P.spread ? P.njobs : 1);
+    c->grid = c->cg * (units < ctas ? units : ctas);
   }
   if (fuse == 1) SGA_TRY(igdn_fwd_set_attr(g.Cout, c->cg));
   else SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout, c->cg), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -33,6 +33,7 @@ struct alignas(64) TcParams {
   int n_spatial;          // tiles per job = N * tiles_h * tiles_w * n_tiles_n (identical for all jobs of a plan)
   int n_sp;               // spatial tiles per job and N tile = N * tiles_h * tiles_w
   int n_sp_pairs;         // CTA-pair mode: ceil(n_sp / 2)
+  int spread;             // small problem: spread the output phases over the grid (decode_slot)
   int relu;
   int dbg;                // development aid (env SGA_DBG): bit 3 = per-role wait-cycle accounting printed by two CTAs
   int mix_at0, mix_at1;   // fused: k-step (in eighths of the main loop) where the mixing halves of the previous tile go
@@ -50,21 +51,32 @@ struct alignas(64) TcParams {
 
 struct TileCoord { int job, img, h0, w0, n0; };
 
-// slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G)
+// slot = blockIdx.x + k * gridDim.x: wave k handles phase (k % njobs) of spatial tiles [(k / njobs) * G, +G), so the
+// phases of a transposed conv re-read their shared input from L2 and every CTA gets the same mix of 9/6/6/4-tap tiles.
+// Small problems (fewer units than CTAs, P.spread): the phases are spread over the grid instead, unit L = k*G + cta ->
+// (spatial L / njobs, phase L % njobs), so that a 12-tile layer occupies 12 CTA pairs once rather than 3 pairs 4 times.
 // CG = 2: the unit is a pair of horizontally adjacent spatial tiles sharing the N tile; a pair whose second tile does
 // not exist still runs it with img = N (TMA zero-fills the loads, nothing is stored).
 template <int CG>
 __device__ __forceinline__ bool decode_slot(const TcParams& P, int k, uint32_t rank, TileCoord& tc_) {
-  const int jb = k % P.njobs;
+  const int g = static_cast<int>(gridDim.x) / CG, cta = static_cast<int>(blockIdx.x) / CG;
+  const int units = (CG == 1) ? P.n_spatial : P.n_sp_pairs * P.n_tiles_n;
+  int jb, u;
+  if (P.spread) {
+    const int L = k * g + cta;
+    if (L >= units * P.njobs) return false;
+    jb = L % P.njobs;
+    u = L / P.njobs;
+  } else {
+    jb = k % P.njobs;
+    u = (k / P.njobs) * g + cta;
+    if (u >= units) return false;
+  }
   int sp, nt;
   if (CG == 1) {
-    int t = (k / P.njobs) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-    if (t >= P.n_spatial) return false;
-    nt = t % P.n_tiles_n;
-    sp = t / P.n_tiles_n;
+    nt = u % P.n_tiles_n;
+    sp = u / P.n_tiles_n;
   } else {
-    const int u = (k / P.njobs) * static_cast<int>(gridDim.x >> 1) + static_cast<int>(blockIdx.x >> 1);
-    if (u >= P.n_sp_pairs * P.n_tiles_n) return false;
     nt = u / P.n_sp_pairs;
     sp = (u % P.n_sp_pairs) * 2 + static_cast<int>(rank);
   }
@@ -82,6 +94,7 @@ template <int CG>
 __device__ __forceinline__ int num_waves(const TcParams& P) {
   const int units = (CG == 1) ? P.n_spatial : P.n_sp_pairs * P.n_tiles_n;
   const int g = static_cast<int>(gridDim.x) / CG;
+  if (P.spread) return (units * P.njobs + g - 1) / g;
   return ((units + g - 1) / g) * P.njobs;
 }
 
