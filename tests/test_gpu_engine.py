@@ -178,3 +178,25 @@ def test_bf16_loop_deviation_is_below_the_seed_to_seed_spread():
     spread = np.max([np.abs(f[i] - f[j]) for i in range(4) for j in range(i)], axis=0)
     dev = np.abs(b - f[0])
     assert (dev <= 1.0 * spread + np.array([1e-3, 0.01])).all(), (dev, spread)
+
+
+def test_grad_bf16_wave_ordered_schedule(monkeypatch):
+    """Layers with at least as many units as CTA pairs walk the output phases wave by wave; smaller ones spread them over
+    the grid (conv_tc.cuh decode_slot).  The parity shapes above are all small, so force the wave order on one of them
+    (SGA_NO_SMALL is read when the engine plans its kernels) and run a shape large enough to take it by itself."""
+    C, n, h, w = 64, 2, 256, 192
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=C + 1)
+    ref = O.sga_graph(x, y, z, Wt, 0.35, O.draw_noise(y, z, 3, 11), 0.01)
+    monkeypatch.setenv("SGA_NO_SMALL", "1")
+    eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
+    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
+    monkeypatch.delenv("SGA_NO_SMALL")
+    C, n, h, w = 64, 10, 256, 256                        # gs2: 10 * 4096 / 128 = 320 tiles per phase >= 74 pairs
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=5)
+    ref = O.sga_graph(x, y, z, Wt, 0.35, O.draw_noise(y, z, 3, 11), 0.01)
+    eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
+    s = eng.unpack_stats(stats.cpu().numpy())
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-3 * abs(float(ref["train_bpp"]))
+    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
