@@ -57,29 +57,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// cluster-scope acquire: for barriers whose arrivals come from the peer CTA of a pair
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("sga_b200: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
-  }
-}
-
 // one lane of a converged warp (always the same one); lets the compiler issue the uniform-datapath instructions
 // (UTMALDG / UTCHMMA / UTCBAR) without a per-instruction election loop
 __device__ __forceinline__ bool elect_one() {
@@ -166,20 +143,6 @@ __device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-
-// TMA store of a 4-D box from shared memory (bulk async-group completion); out-of-bounds parts of the box are clipped
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all bulk groups of this thread have finished READING their shared-memory source
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// byte offset of 16-byte chunk `c16` (0..3) of row `r` inside a SWIZZLE_64B tile with 64-byte rows
-__device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c16) { return r * 64u + ((c16 ^ ((r >> 1) & 3u)) << 4); }
 
 // ---------------- TMEM ----------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {  // whole warp
