@@ -10,6 +10,8 @@ adam_ref.npz   -- trajectories of the reference's own numpy Adam (/root/referenc
 sga_c16.npz    -- the oracle's (oracle/sga_oracle.py) outputs on a tiny seeded case: per-step loss / gradients and the
                   final hard-rounded evaluation.  Pins the oracle against accidental edits and gives the CUDA fp32
                   path a fixed target that does not need the oracle at run time.
+bb_c16.npz     -- the same for the bits-back variant (oracle/bb_oracle.py): 3 R-D steps over [y, z_mean, z_logvar], 3 rate
+                  steps with y_tilde = round(y), the final evaluation (bb_sga.py:200-273), Philox + Box-Muller noise.
 """
 import os
 import sys
@@ -68,7 +70,47 @@ def make_sga():
         y_final=y.numpy(), z_final=z.numpy(), **{"eval_" + k: v.numpy() for k, v in ev.items()})
 
 
+def make_bb():
+    import sga_b200
+    from oracle import bb_oracle as B
+    from oracle import sga_oracle as O
+    C, n, h, w, its, r_its, lmbda, seed = 16, 2, 64, 48, 3, 3, 0.01, 7
+    W = sga_b200.weights.make_synthetic_bb(C, seed)
+    Wt = O._to(W, torch.float32)
+    x = torch.from_numpy(sga_b200.synth.synthetic_images(n, h, w, seed).astype(np.float32) / 255.0)
+    Wa = dict(Wt)
+    Wa["hyper_analysis_transform/layer_2/kernel"] = Wt["hyper_analysis_transform/layer_2/kernel"][..., :C]
+    y, _ = O.analysis(x, Wa)                                              # y_init (bb_sga.py:203)
+    zm, zl = B.hyper_analysis(y, Wt)                                      # bb_sga.py:204
+    opt = O.Adam(lr=0.005)
+    rd, bpp = [], []
+    g0 = None
+    for it in range(its):
+        T = O.annealed_temperature(it, r=0.2, ub=0.5, scheme="exp0", t0=1)
+        uy = O.draw_noise(y, y[..., :1], seed, it)[:2]
+        out = B.bb_graph(x, y, zm, zl, Wt, T, uy, B.draw_eps(zm, seed, it), lmbda)
+        if it == 0:
+            g0 = out
+        rd.append(float(out["rd_loss"])); bpp.append(float(out["train_bpp"]))
+        y, zm, zl = opt.update([y, zm, zl], [out["grad_y"], out["grad_z_mean"], out["grad_z_logvar"]])
+    yt = torch.round(y)
+    zm, zl = B.hyper_analysis(yt, Wt)                                     # bb_sga.py:247
+    opt = O.Adam(lr=0.003)
+    rate = []
+    for it in range(r_its):
+        out = B.bb_graph(x, yt, zm, zl, Wt, 1.0, None, B.draw_eps(zm, seed, its + it), lmbda, rate_only=True)
+        rate.append(float(out["train_bpp"]))
+        zm, zl = opt.update([zm, zl], [out["grad_z_mean"], out["grad_z_logvar"]])
+    ev = B.bb_eval(x, yt, zm, zl, B.draw_eps(zm, seed, its + r_its), Wt)
+    np.savez_compressed(
+        os.path.join(HERE, "bb_c16.npz"), C=C, n=n, h=h, w=w, its=its, r_its=r_its, lmbda=lmbda, seed=seed, annealing_rate=0.2,
+        t0=1, rd_loss=np.array(rd), train_bpp=np.array(bpp), rate=np.array(rate), grad_y0=g0["grad_y"].numpy(),
+        grad_z_mean0=g0["grad_z_mean"].numpy(), grad_z_logvar0=g0["grad_z_logvar"].numpy(), y_tilde=yt.numpy(),
+        z_mean_final=zm.numpy(), z_logvar_final=zl.numpy(), **{"eval_" + k: v.numpy() for k, v in ev.items()})
+
+
 if __name__ == "__main__":
     make_adam()
     make_sga()
+    make_bb()
     print("golden fixtures written to", HERE)

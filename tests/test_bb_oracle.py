@@ -74,3 +74,24 @@ def test_bb_graph_runs_and_rate_only_matches_rd_with_zero_lambda():
     assert torch.allclose(full["grad_z_logvar"], r["grad_z_logvar"], rtol=1e-8, atol=1e-12)
     ev = B.bb_eval(x, yt, zm, zl, eps, W)
     assert torch.allclose(ev["est_bpp"], r["y_bpp"] + r["z_bpp"] - r["bpp_back"], rtol=1e-10)
+
+
+def test_golden_bb_fixture_reproduces():
+    """tests/golden/bb_c16.npz (made by make_golden.py in the authoring container) pins the bits-back oracle."""
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gdir)
+    import make_golden as G
+    gold = dict(np.load(os.path.join(gdir, "bb_c16.npz")))
+    here = G.HERE
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        G.HERE = tmp
+        try:
+            G.make_bb()
+        finally:
+            G.HERE = here
+        new = dict(np.load(os.path.join(tmp, "bb_c16.npz")))
+    for k in ("rd_loss", "train_bpp", "rate", "eval_est_bpp", "eval_psnr", "grad_y0", "grad_z_logvar0"):
+        assert np.allclose(new[k], gold[k], rtol=2e-4, atol=1e-7), k

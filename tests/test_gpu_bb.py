@@ -127,3 +127,38 @@ def test_bb_loop_runs_and_reduces_rate():
         eng.step(None, st, 1.0, it, 0.003, eps_z=eps, rate_only=True, want_stats=False)
     bpp1 = float(eng.grad(None, y_tilde, st["z_mean"], st["z_logvar"], 1.0, 0, eps_z=eps, rate_only=True)[3][2])
     assert bpp1 < bpp0, (bpp0, bpp1)
+
+
+def test_golden_bb_fixture_f32():
+    """Both loops of bb_sga.py:200-273 on the device in fp32 with the Philox / Box-Muller stream against the committed
+    fixture tests/golden/bb_c16.npz (no oracle at run time)."""
+    import os
+    from sga_b200.schedule import annealed_temperature
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bb_c16.npz"))
+    C, n, h, w, its, r_its, seed = (int(gold[k]) for k in ("C", "n", "h", "w", "its", "r_its", "seed"))
+    lmbda = float(gold["lmbda"])
+    W = sga_b200.weights.make_synthetic_bb(C, seed)
+    x = torch.from_numpy(sga_b200.synth.synthetic_images(n, h, w, seed).astype(np.float32) / 255.0).cuda()
+    eng = _engine(W, n, h, w, C, lmbda, "f32", seed=seed)
+    y = eng.encode_init(x)
+    zm, zl = eng.hyper_init(y)
+    gy, gm, gl, _ = eng.grad(x, y, zm, zl, annealed_temperature(0, r=0.2, ub=0.5, scheme="exp0", t0=1), 0)
+    assert rel_err(gy, gold["grad_y0"]) < 3e-4 and rel_err(gm, gold["grad_z_mean0"]) < 5e-4
+    assert rel_err(gl, gold["grad_z_logvar0"]) < 5e-4
+    st = eng.new_state(y, zm, zl)
+    for it in range(its):
+        T = annealed_temperature(it, r=float(gold["annealing_rate"]), ub=0.5, scheme="exp0", t0=int(gold["t0"]))
+        eng.step(x, st, T, it, 0.005)
+        s = eng.unpack_stats(eng.stats.cpu().numpy())
+        assert abs(s["rd_loss"] - gold["rd_loss"][it]) <= 2e-4 * abs(gold["rd_loss"][it]), it
+    y_tilde = torch.round(st["y"])
+    assert (y_tilde.cpu().numpy() != gold["y_tilde"]).mean() < 1e-3          # a rounding tie may flip an element
+    zm, zl = eng.hyper_init(y_tilde)
+    st2 = eng.new_state(y_tilde, zm, zl)
+    for it in range(r_its):
+        eng.step(None, st2, 1.0, its + it, 0.003, rate_only=True, adam_iterations=it)
+        s = eng.unpack_stats(eng.stats.cpu().numpy())
+        assert abs(s["train_bpp"] - gold["rate"][it]) <= 5e-4 * abs(gold["rate"][it]), it
+    ev = eng.eval(x, y_tilde, st2["z_mean"], st2["z_logvar"], step=its + r_its)
+    assert np.abs(ev["est_bpp"] - gold["eval_est_bpp"]).max() < 1e-3          # north_star tolerance: 1e-3 bpp
+    assert np.abs(ev["psnr"] - gold["eval_psnr"]).max() < 0.01                # 0.01 dB
