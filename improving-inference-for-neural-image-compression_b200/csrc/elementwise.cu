@@ -392,8 +392,9 @@ __global__ void k_zbb_path(const float* __restrict__ z_mean, const float* __rest
 
 // g_mean = g_zt_rate + g_hyper;  g_logvar = g_mean * dz_tilde/dlogvar - rate_scale/2   (d log q / d logvar = -1/2 enters
 // the loss with +rate_scale: eval_bpp = ... - bpp_back, bpp_back = -sum log q / (ln2 HW))
-__global__ void k_bb_grads(const float* __restrict__ g_rate, const float* __restrict__ g_hyper, const float* __restrict__ dzl,
-                           long long numel, float half_scale, float* __restrict__ g_mean, float* __restrict__ g_lv) {
+// (no __restrict__: the host passes g_mean = g_rate and g_lv = dzl to update in place)
+__global__ void k_bb_grads(const float* g_rate, const float* __restrict__ g_hyper, const float* dzl, long long numel,
+                           float half_scale, float* g_mean, float* g_lv) {
   ew_pdl_begin();
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (e >= numel) return;
