@@ -95,7 +95,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", sel, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
