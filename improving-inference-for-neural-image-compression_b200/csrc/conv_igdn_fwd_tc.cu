@@ -36,15 +36,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int b_bytes = (NF / CG) * kBlockK * 2;
-  const int ring = P.stages * (kABytes + b_bytes);
+  // operand ring: stages x (A tile | weight tile), or -- halo mode -- a ring of halo tiles followed by a ring of weight tiles
+  const int ring = P.halo ? P.a_stages * kHaloBytes + P.stages * b_bytes : P.stages * (kABytes + b_bytes);
   const uint32_t a_base = base;
-  const uint32_t b_base = base + P.stages * kABytes;
+  const uint32_t b_base = base + (P.halo ? P.a_stages * kHaloBytes : P.stages * kABytes);
   const uint32_t a2_base = base + ring;
   uint8_t* a2_ptr = smem + ring;
   const uint32_t g_base = a2_base + kA2Bytes;
   float* s_par = reinterpret_cast<float*>(smem + ring + kA2Bytes + kGBytes);       // bias[NF] | beta[NF]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 2 * NF);
-  // full[8] | empty[8] | tfull[2] | tempty[2] | a2full | a2empty | nfull[2] | nempty[2] | gbar
+  // full[8] | empty[8] | tfull[2] | tempty[2] | a2full | a2empty | nfull[2] | nempty[2] | gbar | afull[2] | aempty[2]
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
@@ -54,8 +55,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
   const uint32_t bar_nfull = bar_a2empty + 8;
   const uint32_t bar_nempty = bar_nfull + 16;
   const uint32_t bar_g = bar_nempty + 16;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 11);
+  const uint32_t bar_afull = bar_g + 8;
+  const uint32_t bar_aempty = bar_afull + 16;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 15);
   const uint32_t lead_full = (CG == 2) ? mapa_shared(bar_full, 0) : bar_full;
+  const uint32_t lead_afull = (CG == 2) ? mapa_shared(bar_afull, 0) : bar_afull;
   const uint32_t lead_tempty = (CG == 2) ? mapa_shared(bar_tempty, 0) : bar_tempty;
   const uint32_t lead_a2full = (CG == 2) ? mapa_shared(bar_a2full, 0) : bar_a2full;
   const uint32_t lead_nempty = (CG == 2) ? mapa_shared(bar_nempty, 0) : bar_nempty;
@@ -84,6 +88,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
     mbar_init(bar_a2full, 4 * CG);
     mbar_init(bar_a2empty, 1);
     mbar_init(bar_g, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_afull + 8 * b, 1);
+      mbar_init(bar_aempty + 8 * b, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -121,10 +129,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
     uint32_t phase = 0;
     const uint32_t stage_tx = static_cast<uint32_t>(CG * (kABytes + b_bytes));
     const int b_row_off = static_cast<int>(rank) * (NF / 2);
+    int astage = 0;
+    uint32_t aphase = 0;
     for (int w = 0; w < nwaves; ++w) {
       TileCoord tc_;
       if (!decode_slot<CG>(P, w, rank, tc_)) continue;
       const TcJob& J = P.job[tc_.job];
+      if (P.halo) {
+        for (int gi = 0; gi < J.ngroups; ++gi) {
+          const TcGroup grp_ = P.groups[J.group_begin + gi];
+          const CUtensorMap* am = &P.amap[grp_.view];
+          const int ax = tc_.w0 + grp_.ox, ay = tc_.h0 + grp_.oy;
+          for (int kc = 0; kc < P.kchunks; ++kc) {
+            mbar_wait(bar_aempty + 8 * astage, aphase ^ 1u);       // the halo tile of this (view, K chunk): all its taps share it
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(bar_afull + 8 * astage, CG * kHaloBytes);
+              if (CG == 2) tma_load_4d_cg2(a_base + astage * kHaloBytes, am, lead_afull + 8 * astage, kc * kBlockK, ax, ay, tc_.img);
+              else tma_load_4d(a_base + astage * kHaloBytes, am, bar_afull + 8 * astage, kc * kBlockK, ax, ay, tc_.img);
+            }
+            if (++astage == P.a_stages) { astage = 0; aphase ^= 1u; }
+            for (int t = 0; t < grp_.ntaps; ++t) {
+              const int brow = P.htaps[grp_.tap_begin + t].widx * P.Nn + (CG == 2 ? b_row_off : 0);
+              SGA_TIMED(0, mbar_wait(bar_empty + 8 * stage, phase ^ 1u));
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, static_cast<uint32_t>(CG * b_bytes));
+                if (CG == 2) tma_load_2d_cg2(b_base + stage * b_bytes, &P.bmap, lead_full + 8 * stage, kc * kBlockK, brow);
+                else tma_load_2d(b_base + stage * b_bytes, &P.bmap, bar_full + 8 * stage, kc * kBlockK, brow);
+              }
+              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        continue;
+      }
       for (int t = 0; t < J.ntaps; ++t) {
         const Tap tap = P.taps[J.tap_begin + t];
         const CUtensorMap* am = &P.amap[tap.view];
@@ -157,7 +194,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
       auto commit = [](uint32_t bar) { if (CG == 2) umma_commit_cg2_both(bar); else umma_commit(bar); };
       const uint64_t adesc0 = smem_desc_sw128(a_base), bdesc0 = smem_desc_sw128(b_base), a2desc0 = smem_desc_sw128(a2_base),
                      gdesc0 = smem_desc_sw128(g_base);
+      const uint64_t ahalo0 = smem_desc_sw128_sbo(a_base, kHaloPitch * 128);
       const uint32_t a_step = kABytes >> 4, b_step = static_cast<uint32_t>(b_bytes) >> 4;
+      int astage = 0;
+      uint32_t aphase = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;          // tiles issued
@@ -202,6 +242,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
         SGA_TIMED(1, mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u));
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * NF;
+        if (P.halo) {
+          const TcJob& J = P.job[tc_.job];
+          int k = 0;
+          for (int gi = 0; gi < J.ngroups; ++gi) {
+            const TcGroup grp_ = P.groups[J.group_begin + gi];
+            for (int kc = 0; kc < P.kchunks; ++kc) {
+              SGA_TIMED(0, mbar_wait(bar_afull + 8 * astage, aphase));
+              for (int t = 0; t < grp_.ntaps; ++t, ++k) {
+                const TcHaloTap tap = P.htaps[grp_.tap_begin + t];
+                SGA_TIMED(0, mbar_wait(bar_full + 8 * stage, phase));
+                tcgen05_fence_after();
+                if (elect_one()) {
+                  // window of this tap inside the halo tile: start row dy'*16 + dx', 8-row groups 2048 B apart
+                  const uint64_t ad = ahalo0 + static_cast<uint64_t>(astage * (kHaloBytes >> 4) + tap.a_off16) +
+                                      (static_cast<uint64_t>(tap.boff) << 49);
+                  const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * b_step);
+#pragma unroll
+                  for (int kk = 0; kk < kBlockK / 16; ++kk) mma(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                  commit(bar_empty + 8 * stage);
+                }
+                if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                if (mpart < NP) mix_advance(false);
+              }
+              if (elect_one()) commit(bar_aempty + 8 * astage);     // halo tile free after its last tap
+              if (++astage == P.a_stages) { astage = 0; aphase ^= 1u; }
+            }
+          }
+        } else
         for (int k = 0; k < nk; ++k) {
           SGA_TIMED(0, mbar_wait(bar_full + 8 * stage, phase));
           tcgen05_fence_after();

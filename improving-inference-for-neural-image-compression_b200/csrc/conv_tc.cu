@@ -558,6 +558,11 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   // spatial tile: 128 pixels = TH x TW
   const int Wo0 = plan.job[0].Wo;
   P.TW = (Wo0 >= 16) ? 16 : 8;
+  // experimental (SGA_HALO=2): halo-tile A reuse in the fused forward kernel; SGA_HALO=1 sets the descriptor base_offset
+  // from the window start and is WRONG on this hardware (the operand swizzle follows absolute address bits) -- kept only
+  // as the record of that experiment
+  if (const char* eh = getenv("SGA_HALO")) P.halo = (fuse == 1) ? atoi(eh) : 0;
+  if (P.halo) P.TW = 8;                               // one 8-row operand group per tile row
   P.TH = kBlockM / P.TW;
   P.tiles_h = ceil_div(plan.job[0].Ho, P.TH);
   P.tiles_w = ceil_div(plan.job[0].Wo, P.TW);
@@ -585,16 +590,52 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
   const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
+  P.a_stages = 0;
+  if (P.halo) {                                       // halo ring (A) + weight ring (B)
+    P.a_stages = 2;
+    stages = (227 * 1024 - fixed - P.a_stages * kHaloBytes) / b_bytes;
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* es = getenv("SGA_DBG_STAGES")) { const int v = atoi(es); if (v >= 2 && v < stages) stages = v; }
   SGA_CHECK(stages >= 2, "not enough shared memory for the pipeline");
   P.stages = stages;
-  c->smem_bytes = fixed + stages * (kABytes + b_bytes);
-  int ntap = 0;
+  c->smem_bytes = P.halo ? fixed + P.a_stages * kHaloBytes + stages * b_bytes : fixed + stages * (kABytes + b_bytes);
+  int ntap = 0, ngroup = 0;
   for (int jn = 0; jn < plan.njobs; ++jn) {
     const ConvJobPlan& jp = plan.job[jn];
     TcJob& J = P.job[jn];
     J.tap_begin = ntap; J.ntaps = jp.ntaps;
+    if (P.halo) {
+      // group the taps by input view; the halo tile of a group starts at the smallest (dy, dx) of its taps
+      J.group_begin = ngroup; J.ngroups = 0;
+      int nh = ntap;
+      for (int v = 0; v < jp.nviews; ++v) {
+        int ox = 1 << 30, oy = 1 << 30, mx = -(1 << 30), my = -(1 << 30), cnt = 0;
+        for (int t = 0; t < jp.ntaps; ++t) {
+          if (jp.taps[t].view != v) continue;
+          ++cnt;
+          ox = jp.taps[t].dx < ox ? jp.taps[t].dx : ox; oy = jp.taps[t].dy < oy ? jp.taps[t].dy : oy;
+          mx = jp.taps[t].dx > mx ? jp.taps[t].dx : mx; my = jp.taps[t].dy > my ? jp.taps[t].dy : my;
+        }
+        if (cnt == 0) continue;
+        if (mx - ox + 8 > kHaloPitch || my - oy + 16 > kHaloRows || ngroup >= kMaxGroups) {
+          delete c;
+          set_error("tcgen05 conv: taps of view %d span more than the halo tile holds", v);
+          return SGA_ERR_INVALID;
+        }
+        TcGroup& Gp = P.groups[ngroup++];
+        Gp.view = v; Gp.ox = ox; Gp.oy = oy; Gp.tap_begin = nh; Gp.ntaps = cnt;
+        for (int t = 0; t < jp.ntaps; ++t) {
+          if (jp.taps[t].view != v) continue;
+          TcHaloTap& T = P.htaps[nh++];
+          T.widx = jp.taps[t].widx;
+          const int ry = jp.taps[t].dy - oy, rx = jp.taps[t].dx - ox;
+          T.a_off16 = static_cast<uint32_t>((ry * kHaloPitch + rx) * 128) >> 4;
+          T.boff = (P.halo == 1) ? static_cast<uint32_t>(rx & 7) : 0u;
+        }
+        ++J.ngroups;
+      }
+    }
     for (int t = 0; t < jp.ntaps; ++t) P.taps[ntap++] = jp.taps[t];
     J.Ho = jp.Ho; J.Wo = jp.Wo;
     J.out_off = (jp.out_phase_stride == 2) ? (static_cast<long long>(jp.out_py) * g.Wout + jp.out_px) * g.Cout : 0;
@@ -611,7 +652,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
                               static_cast<uint64_t>((g.Hin - py + s - 1) / s), static_cast<uint64_t>(g.N)};
     const uint64_t strides[3] = {static_cast<uint64_t>(s) * g.Cin * 2, static_cast<uint64_t>(s) * g.Win * g.Cin * 2,
                                  static_cast<uint64_t>(g.Hin) * g.Win * g.Cin * 2};
-    const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(P.TW), static_cast<uint32_t>(P.TH), 1};
+    const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(P.halo ? kHaloPitch : P.TW),
+                             static_cast<uint32_t>(P.halo ? kHaloRows : P.TH), 1};
     const __nv_bfloat16* basep = x + (static_cast<long long>(py) * g.Win + px) * g.Cin;
     int st = tma_encode_tiled(&P.amap[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, basep, dims, strides, box,
                               CU_TENSOR_MAP_SWIZZLE_128B);

@@ -14,7 +14,17 @@ constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 
+// halo-tile A reuse (forward fusion, opt-in): one box {64 ch, 16, 18, 1} -- the 8 x 16-pixel tile plus its halo, padded to a
+// 16-pixel row pitch -- per (input view, K chunk); every tap of the view addresses its window inside it: M row r =
+// pixel (r/8, r%8) sits at byte ((r/8 + dy')*16 + dx' + r%8)*128, i.e. 8-row groups 2048 B apart (descriptor SBO)
+constexpr int kHaloPitch = 16, kHaloRows = 18;
+constexpr int kHaloBytes = kHaloPitch * kHaloRows * 64 * 2;   // 36 KB
+constexpr int kMaxGroups = 16;
+struct TcHaloTap { int widx; uint32_t a_off16; uint32_t boff; };        // weight slice, (window byte offset) >> 4, start row & 7
+struct TcGroup { int view, ox, oy, tap_begin, ntaps; };                 // taps reading one input view; halo origin (ox, oy)
+
 struct TcJob {
+  int group_begin, ngroups;
   int tap_begin, ntaps;
   int Ho, Wo;             // pixel grid of the output view
   long long out_off;      // element offset of the output view
@@ -27,6 +37,10 @@ struct alignas(64) TcParams {
   CUtensorMap gmap;       // fused IGDN: channel-mixing operand [n][k] bf16, box {64, N/2}
   TcJob job[4];
   Tap taps[kMaxTaps];
+  TcGroup groups[kMaxGroups];
+  TcHaloTap htaps[kMaxTaps];
+  int halo;               // 0 = off; 1 = descriptor base_offset from the window start; 2 = base_offset 0
+  int a_stages;           // halo tiles in flight
   int njobs, N, K, Nn;
   int block_n, n_tiles_n, kchunks, stages;
   int TH, TW, tiles_h, tiles_w;

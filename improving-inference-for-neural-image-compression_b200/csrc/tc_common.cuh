@@ -235,6 +235,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // layout type SWIZZLE_128B [61,64)
   return d;
 }
+// same with an explicit stride between the 8-row groups (rows of a group stay 128 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // K-major operand, no swizzle ("interleave"): 8-row x 16-byte core matrices (128 contiguous bytes);
 // lbo = byte distance between the two core matrices of one K=16 slice, sbo = between 8-row groups.
 __device__ __forceinline__ uint64_t smem_desc_interleave(uint32_t addr, uint32_t lbo, uint32_t sbo) {

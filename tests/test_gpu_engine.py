@@ -200,3 +200,18 @@ def test_grad_bf16_wave_ordered_schedule(monkeypatch):
     s = eng.unpack_stats(stats.cpu().numpy())
     assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-3 * abs(float(ref["train_bpp"]))
     assert rms_rel_err(gy, ref["grad_y"]) < 3e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
+
+
+def test_grad_bf16_halo_tile_operand_windows(monkeypatch):
+    """Opt-in forward path (SGA_HALO=2): one 16x18-pixel halo box per (view, K chunk), every tap addressing its window
+    through an un-aligned SWIZZLE_128B descriptor start (base_offset 0: the swizzle follows absolute address bits)."""
+    monkeypatch.setenv("SGA_HALO", "2")
+    for C, n, h, w in ((192, 2, 256, 256), (64, 3, 48, 80)):
+        W, Wt, x, y, z = make_case(C, n, h, w, seed=C + 1)
+        ref = O.sga_graph(x, y, z, Wt, 0.35, O.draw_noise(y, z, 3, 11), 0.01)
+        eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
+        gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
+        s = eng.unpack_stats(stats.cpu().numpy())
+        assert abs(s["train_mse"] - float(ref["train_mse"])) <= 5e-3 * abs(float(ref["train_mse"]))
+        assert rms_rel_err(gy, ref["grad_y"]) < 3e-2
+        eng.close()
