@@ -13,8 +13,9 @@ class SgaConfig(ctypes.Structure):
     _fields_ = [
         ("n_images", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
         ("num_filters", ctypes.c_int32), ("n_ref", ctypes.c_int32), ("operand", ctypes.c_int32),
-        ("lmbda", ctypes.c_float), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
-        ("adam_eps", ctypes.c_float), ("clip_eps", ctypes.c_float), ("seed", ctypes.c_uint64),
+        ("lmbda", ctypes.c_float), ("clip_eps", ctypes.c_float),
+        ("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("adam_eps", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
         ("first_image", ctypes.c_int32), ("variant", ctypes.c_int32),
     ]
 
@@ -68,7 +69,8 @@ def load():
         raise SgaError("libsga_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "or `python %s/build.py`. There is no CPU fallback." % (LIB_PATH, HERE))
     lib = ctypes.CDLL(LIB_PATH)
-    vp, i32, i64, f32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64
+    vp, i32, i64, f32, u64, f64 = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64,
+                                   ctypes.c_double)
     lib.sga_last_error.restype = ctypes.c_char_p
     lib.sga_last_error.argtypes = []
     lib.sga_version.restype = ctypes.c_int
@@ -90,13 +92,13 @@ def load():
     lib.sga_op_soft_round.argtypes = [vp, vp, i64, f32, f32, u64, i32, i32, vp, vp, vp]
     lib.sga_op_eb_likelihood.argtypes = [vp, i64, i32, vp * 4, vp * 4, vp * 3, vp, vp, vp]
     lib.sga_op_gauss_likelihood.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
-    lib.sga_op_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
+    lib.sga_op_adam.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, vp]
     lib.sga_op_conv.argtypes = [i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.sga_op_gdn.argtypes = [i32, i32, vp, vp, vp, i64, i32, vp, vp, vp]
     lib.sga_op_igdn_bwd.argtypes = [i32, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.sga_bb_hyper_init.argtypes = [vp, vp, vp, vp, vp]
     lib.sga_bb_grad.argtypes = [vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
-    lib.sga_bb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, i32, f32, vp, vp]
+    lib.sga_bb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, i32, f64, vp, vp]
     lib.sga_bb_eval.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("sga_last_error", "sga_workspace_bytes", "sga_launch_count"):

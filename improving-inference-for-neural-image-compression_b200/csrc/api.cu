@@ -595,7 +595,7 @@ int sga_bb_grad(sga_ctx* c, const float* x, const float* y, const float* z_mean,
 
 int sga_bb_step(sga_ctx* c, const float* x, float* y, float* z_mean, float* z_logvar, float* m_y, float* v_y, float* m_zm,
                 float* v_zm, float* m_zl, float* v_zl, float T, int32_t step, int32_t adam_iterations, const float* noise_y,
-                const float* eps_z, int32_t rate_only, float lr, float* stats, void* stream) {
+                const float* eps_z, int32_t rate_only, double lr, float* stats, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const BbArgs bb{z_mean, z_logvar, eps_z, rate_only ? 1 : 0, rate_only ? 1 : 0};
   SGA_TRY(bb_grad_common(c, x, y, bb, T, step, noise_y, stats, st));
@@ -713,8 +713,8 @@ int sga_op_gauss_likelihood(const float* yt, const float* mu, const float* ls, i
   return launch_gauss_likelihood(yt, mu, ls, numel, p, dpdy, dpdsb, static_cast<cudaStream_t>(stream));
 }
 
-int sga_op_adam(float* p, float* m, float* v, const float* g, int64_t numel, float lr, float beta1, float beta2,
-                float eps, int32_t iterations, void* stream) {
+int sga_op_adam(float* p, float* m, float* v, const float* g, int64_t numel, double lr, double beta1, double beta2,
+                double eps, int32_t iterations, void* stream) {
   return launch_adam(p, m, v, g, nullptr, nullptr, numel, lr, beta1, beta2, eps, iterations, nullptr,
                      static_cast<cudaStream_t>(stream));
 }

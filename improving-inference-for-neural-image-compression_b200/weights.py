@@ -159,34 +159,29 @@ def gdn_to_reparam(var, minimum):
 
 
 def irdft_matrix(shape):
-    """Orthonormal real-DFT synthesis basis: (prod(shape), prod(shape)) matrix M with
-    kernel = reshape(M @ kernel_rdft, shape + (Cin, Cout)) (tfc.RDFTParameterizer).
-    UNVERIFIED against tfc 1.3's column ordering (PARITY_ASSUMPTIONS.md item P9): real checkpoints
-    must be validated before trusting this path."""
+    """Orthonormal real-DFT synthesis basis of tfc's RDFTParameterizer (spectral_ops.irdft_matrix, tfc 1.3): a
+    (prod(shape), prod(shape)) matrix M with kernel = reshape(M @ kernel_rdft, shape + (Cin, Cout)).
+
+    The basis is SEPARABLE, built one axis at a time: rfft along the axis, the non-DC (and, for even lengths,
+    non-Nyquist) bins scaled by sqrt(2), everything divided by sqrt(n_axis), then the real parts of all bins followed by
+    the imaginary parts of the scaled bins are concatenated along that same axis (n real coefficients again), and the next
+    axis is transformed.  Rows index the flattened spatial position, columns the flattened (per-axis) coefficients.
+    Pinned in tests/test_host.py by hand-computed columns; still unchecked against a TF-written checkpoint
+    (PARITY_ASSUMPTIONS.md item P9)."""
     shape = tuple(int(s) for s in shape)
     size = int(np.prod(shape))
     rank = len(shape)
-    eye = np.identity(size, dtype=np.float64).reshape((size,) + shape)
-    spec = np.fft.rfftn(eye, axes=tuple(range(1, rank + 1)))
-    last = shape[-1]
-    scale = np.ones(spec.shape[-1])
-    scale[1:(last - 1) // 2 + 1] = np.sqrt(2.0)
-    spec = spec * scale / np.sqrt(size)
-    spec = spec.reshape(size, -1)
-    cols = np.concatenate([spec.real, spec.imag], axis=1)
-    # keep a maximal linearly independent set of columns, in order (Gram-Schmidt pivoting)
-    keep, basis = [], []
-    for j in range(cols.shape[1]):
-        v = cols[:, j].copy()
-        for b in basis:
-            v -= b * (b @ v)
-        n = np.linalg.norm(v)
-        if n > 1e-9:
-            basis.append(v / n)
-            keep.append(j)
-        if len(keep) == size:
-            break
-    return np.stack(basis, axis=1)
+    m = np.identity(size, dtype=np.float64).reshape((size,) + shape)
+    for axis in range(rank):
+        n = shape[axis]
+        spec = np.fft.rfft(m, axis=axis + 1)
+        sl = [slice(None)] * (rank + 1)
+        sl[axis + 1] = slice(1, None) if n % 2 == 1 else slice(1, -1)
+        sl = tuple(sl)
+        spec[sl] *= np.sqrt(2.0)
+        spec /= np.sqrt(n)
+        m = np.concatenate([spec.real, spec[sl].imag], axis=axis + 1)
+    return m.reshape(size, size)
 
 
 def deparameterise(raw, shapes=None):

@@ -54,8 +54,9 @@ typedef struct {
                               means over it (sga.py:147,150), so every gradient carries 1/n_ref */
   int32_t operand;         /* sga_operand used by sga_step / sga_grad */
   float lmbda;             /* --lambda (sga.py:157-163); <= 0 means rate only */
-  float lr, beta1, beta2, adam_eps;   /* adam.py:9-10 ; sga.py:190 uses lr = 0.005 */
   float clip_eps;          /* epsilon of the atanh clip, 1e-5 (sga.py:30) */
+  double lr, beta1, beta2, adam_eps;  /* adam.py:9-10 ; sga.py:190 uses lr = 0.005.  Python floats in the reference: kept
+                              as doubles so that lr_t and float32(1 - beta) are formed exactly as numpy forms them */
   uint64_t seed;           /* key of the Philox4x32-10 Gumbel noise stream */
   int32_t first_image;     /* index of this shard's first image inside the reference batch: the noise counter is the
                               element index inside the WHOLE batch, so results do not depend on the sharding */
@@ -141,7 +142,7 @@ int sga_bb_grad(sga_ctx* ctx, const float* x, const float* y, const float* z_mea
  * `adam_iterations` is the optimiser's 0-based iteration count (it restarts with the second loop). */
 int sga_bb_step(sga_ctx* ctx, const float* x, float* y, float* z_mean, float* z_logvar, float* m_y, float* v_y,
                 float* m_zm, float* v_zm, float* m_zl, float* v_zl, float temperature, int32_t step,
-                int32_t adam_iterations, const float* noise_y, const float* eps_z, int32_t rate_only, float lr,
+                int32_t adam_iterations, const float* noise_y, const float* eps_z, int32_t rate_only, double lr,
                 float* stats_out, void* stream);
 
 /* eval_tensors of bb_sga.py:176-177 for y_tilde = round(y) (bb_sga.py:271-272), always fp32. */
@@ -179,8 +180,8 @@ int sga_op_eb_likelihood(const float* z_tilde, int64_t numel, int32_t channels, 
 int sga_op_gauss_likelihood(const float* y_tilde, const float* mu, const float* log_sigma, int64_t numel,
                             float* p_out, float* dp_dy, float* dp_dsigma_bounded, void* stream);
 /* a12: Adam (adam.py:36-57), float32 state, lr_t computed on the host in double. */
-int sga_op_adam(float* p, float* m, float* v, const float* g, int64_t numel, float lr, float beta1, float beta2,
-                float eps, int32_t iterations, void* stream);
+int sga_op_adam(float* p, float* m, float* v, const float* g, int64_t numel, double lr, double beta1, double beta2,
+                double eps, int32_t iterations, void* stream);
 /* a4/a7/a14: one (de)conv of nn_models.py. kind: 0 = up2 (corr=False, strides_up=2), 1 = dgrad of up2,
  * 2 = stride-1 true conv (corr=False), 3 = dgrad of 2, 4 = corr stride 2 (strides_down=2), 5 = corr stride 1.
  * kernel (kh,kw,Cin,Cout) in the reference layout; x [n,h,w,cin_of_op]; out [n,ho,wo,cout_of_op];

@@ -102,8 +102,10 @@ def test_adam_matches_reference_golden():
         ops.adam_(p, m, v, torch.from_numpy(gold["grads"][it]).cuda(), 0.005, 0.9, 0.999, 1e-8, it)
         ref = gold["params"][it]
         diff = np.abs(p.cpu().numpy() - ref)
-        # identical operation order; allow 1 ulp from the float32 rounding of lr_t
-        assert diff.max() <= 2 * np.spacing(np.abs(ref).max().astype(np.float32)), (it, diff.max())
+        # identical operation order and hyper-parameters carried as doubles (float32(1 - beta) formed as numpy forms it):
+        # at most 1 ulp PER ELEMENT (a last-bit difference of the host pow() in lr_t), exact for nearly all elements
+        assert (diff <= np.spacing(np.abs(ref).astype(np.float32))).all(), (it, diff.max())
+        assert (diff == 0).mean() > 0.99, (it, (diff == 0).mean())
 
 
 def test_adam_empty():

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.sga_version() >= 100
-    assert ctypes.sizeof(_lib.SgaConfig) == 64
+    assert ctypes.sizeof(_lib.SgaConfig) == 80
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -80,6 +80,24 @@ def test_reparameterised_checkpoint_entries():
     assert np.allclose(W["a/gdn_0/beta"], beta, rtol=1e-6) and np.allclose(W["a/gdn_0/gamma"], gamma, atol=1e-7)
     M = weights.irdft_matrix((5, 5))
     assert M.shape == (25, 25) and np.allclose(M.T @ M, np.eye(25), atol=1e-9)     # orthonormal basis
+    # hand-built 1-D basis of tfc's per-axis construction: [real bins 0..n/2 | imaginary parts of the sqrt(2)-scaled bins]
+    def basis_1d(n):
+        k = np.arange(n)[:, None]
+        nb = n // 2 + 1
+        scaled = list(range(1, nb)) if n % 2 else list(range(1, nb - 1))
+        cols = []
+        for b in range(nb):
+            cols.append(np.cos(2 * np.pi * k * b / n) * (np.sqrt(2.0) if b in scaled else 1.0))
+        for b in scaled:
+            cols.append(-np.sin(2 * np.pi * k * b / n) * np.sqrt(2.0))
+        return np.concatenate(cols, axis=1) / np.sqrt(n)
+    assert np.allclose(weights.irdft_matrix((3,)), [[0.57735027, 0.81649658, 0.0], [0.57735027, -0.40824829, -0.70710678],
+                                                    [0.57735027, -0.40824829, 0.70710678]], atol=1e-7)
+    for n in (2, 3, 4, 5):
+        assert np.allclose(weights.irdft_matrix((n,)), basis_1d(n), atol=1e-12)
+    # 2-D: separable -- row (i, j), column (a, b) = B_h[i, a] * B_w[j, b]
+    assert np.allclose(M, np.kron(basis_1d(5), basis_1d(5)), atol=1e-12)
+    assert np.allclose(weights.irdft_matrix((3, 4)), np.kron(basis_1d(3), basis_1d(4)), atol=1e-12)
     k = rng.standard_normal((5, 5, 2, 3)).astype(np.float32)
     rdft = M.T @ k.reshape(25, 6)
     W = weights.deparameterise({"l/kernel_rdft": rdft, "l/kernel_shape": np.array([5, 5, 2, 3])})
@@ -201,3 +219,55 @@ def test_tf_bundle_roundtrip_and_checkpoint_loading(tmp_path):
     open(prefix + ".index", "wb").write(bytes(bad))
     with pytest.raises(ValueError):
         tf_bundle.read_index(prefix + ".index")
+
+
+def test_msssim_value_against_straight_line_numpy():
+    """sga.py:175-176: tf.image.ssim_multiscale(x_hat, 255 x, 255).  msssim.py (torch, grouped convolutions) against an
+    independent straight-line numpy implementation in the variance / covariance form, on a 192x208 pair (five scales, one
+    odd-sized level that needs the symmetric pad) and on an identical pair (MS-SSIM = 1)."""
+    import torch
+    from sga_b200.msssim import msssim_per_image
+
+    def gauss_window(a, w1d):
+        # separable valid-mode filtering with explicit shifts
+        h = sum(w1d[k] * a[k:a.shape[0] - len(w1d) + 1 + k, :] for k in range(len(w1d)))
+        return sum(w1d[k] * h[:, k:h.shape[1] - len(w1d) + 1 + k] for k in range(len(w1d)))
+
+    def ref_msssim(xh, xr):                                   # [H,W,3] float64, 0..255
+        t = np.arange(11) - 5.0
+        w1d = np.exp(-t * t / (2 * 1.5 ** 2)); w1d /= w1d.sum()
+        c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+        pf = [0.0448, 0.2856, 0.3001, 0.2363, 0.1333]
+        per_ch = []
+        for ch in range(3):
+            a, b = xh[..., ch], xr[..., ch]
+            vals = []
+            for lvl in range(5):
+                if lvl > 0:
+                    if a.shape[0] % 2: a, b = np.vstack([a, a[-1:]]), np.vstack([b, b[-1:]])
+                    if a.shape[1] % 2: a, b = np.hstack([a, a[:, -1:]]), np.hstack([b, b[:, -1:]])
+                    a = 0.25 * (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
+                    b = 0.25 * (b[0::2, 0::2] + b[1::2, 0::2] + b[0::2, 1::2] + b[1::2, 1::2])
+                mu_a, mu_b = gauss_window(a, w1d), gauss_window(b, w1d)
+                var_a = gauss_window(a * a, w1d) - mu_a ** 2
+                var_b = gauss_window(b * b, w1d) - mu_b ** 2
+                cov = gauss_window(a * b, w1d) - mu_a * mu_b
+                cs = (2 * cov + c2) / (var_a + var_b + c2)
+                lum = (2 * mu_a * mu_b + c1) / (mu_a ** 2 + mu_b ** 2 + c1)
+                vals.append(max((lum * cs).mean(), 0.0) if lvl == 4 else max(cs.mean(), 0.0))
+            per_ch.append(np.prod([v ** p for v, p in zip(vals, pf)]))
+        return float(np.mean(per_ch))
+
+    rng = np.random.default_rng(3)
+    h, w = 200, 360                                           # level sizes 200,100,50,25(odd -> padded),13
+    base = rng.random((h // 8, w // 8, 3))
+    x = np.kron(base, np.ones((8, 8, 1)))[:h, :w] * 0.8 + 0.1 * rng.random((h, w, 3))
+    x = np.round(x * 255) / 255.0
+    xt = x + 0.06 * rng.standard_normal(x.shape)
+    got = msssim_per_image(torch.from_numpy(xt[None].astype(np.float32)), torch.from_numpy(x[None].astype(np.float32)))
+    xh = np.round(np.clip(xt.astype(np.float32), 0, 1) * np.float32(255)).astype(np.float64)
+    want = ref_msssim(xh, x.astype(np.float32).astype(np.float64) * 255.0)
+    assert 0.3 < want < 0.999
+    assert abs(float(got[0]) - want) < 2e-6, (float(got[0]), want)
+    same = msssim_per_image(torch.from_numpy(x[None].astype(np.float32)), torch.from_numpy(x[None].astype(np.float32)))
+    assert abs(float(same[0]) - 1.0) < 1e-6
