@@ -1,18 +1,26 @@
-"""bench.py -- SGA iterations/sec on the Kodak-shaped synthetic batch (BASELINE.json: 24x768x512x3, 192 filters,
-lambda 0.01), one process per GPU.
+"""bench.py -- SGA iterations/sec on the reference's workloads, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kodak192|kodak256|tecnick|bb]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one SGA iteration of the whole 24-image batch: Gumbel soft round of y,z -> h_s / g_s forward -> rate +
-distortion -> backward to the latents -> Adam (reference sga.py:211-215).  The batch is sharded by image across the
-ranks (no collective on the data path); the job is fixed as N grows => "scaling": "strong".
+Default workload = BASELINE.json configs[1]: the Kodak-shaped synthetic batch 24x768x512x3, 192 filters, lambda 0.01.
+A "step" is one SGA iteration of the whole batch: Gumbel soft round of y,z -> h_s / g_s forward -> rate + distortion ->
+backward to the latents -> Adam (reference sga.py:211-215).  The batch is sharded by image across the ranks (no collective
+on the data path); the job is fixed as N grows => "scaling": "strong".
 
-Rank 0 prints ONE JSON line.  `value` is device-resident throughput; `e2e` re-measures the same loop through the
-public engine API with the image batch coming from pinned HOST memory every step (sga.py:212-214 feeds x every
-iteration) and the step's statistics read back to the host; `roofline` is the tcgen05 (de)conv kernels' achieved
-TFLOP/s from CUDA events around each of their launches in a second, instrumented pass of the same K steps; `cpu_baseline` is the CPU oracle (a PyTorch-CPU restatement of
-the reference graph -- TF 1.15 is not installable) on a bounded sample.
+Rank 0 prints ONE JSON line.
+  value        device-resident throughput of K iterations through sga_loop (the call the CLI makes: one CUDA graph of
+               the two-stream step, replayed), CUDA events on the launching stream, max over ranks;
+  e2e          the same loop through the public engine API one iteration per call, with the image batch copied from
+               pinned HOST memory every iteration (sga.py:212-214 feeds x every iteration) and the iteration's statistics
+               read back to the host;
+  roofline     the DOMINANT kernel (g_s layer 2 forward: transposed conv + fused inverse GDN): algorithmic FLOPs per launch /
+               its mean launch duration from CUDA event pairs in a third, instrumented pass of the same K iterations;
+               `kernels` lists every launch group of the step the same way (tensor-bound ones against the measured bf16
+               peak, the two layer-3 kernels against the measured HBM bandwidth), `whole_step` the whole iteration;
+  cpu_baseline the CPU restatement of the reference loop (baseline/cpu_sga.py: autograd backward, host Adam, x re-fed
+               every iteration) on the SAME batch, all host cores, 2 timed iterations (N = 1 only);
+  --impl reference   times that CPU arm alone, K timed iterations of the full batch.
 """
 import argparse
 import json
@@ -27,9 +35,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_IMAGES, HEIGHT, WIDTH, C, LMBDA = 24, 768, 512, 192, 0.01
-METRIC = "SGA iters/sec (768x512, 192 filters)"
 UNIT = "it/s"
+WORKLOADS = {
+    # name: images, height, width, filters, lambda, reference batch size, variant, metric label, description
+    "kodak192": dict(n=24, h=768, w=512, c=192, lmbda=0.01, variant="sga", metric="SGA iters/sec (768x512, 192 filters)",
+                     desc="SGA 24x768x512x3, num_filters=192, lambda=0.01 (BASELINE configs[1])"),
+    "kodak256": dict(n=24, h=768, w=512, c=256, lmbda=0.08, variant="sga", metric="SGA iters/sec (768x512, 256 filters)",
+                     desc="SGA 24x768x512x3, num_filters=256, lambda=0.08 (BASELINE configs[2], high-rate model)"),
+    "tecnick": dict(n=100, h=1200, w=1200, c=192, lmbda=0.01, variant="sga", metric="SGA iters/sec (1200x1200, 192 filters)",
+                    desc="SGA Tecnick-shaped 100x1200x1200x3 in reference batches of 7 (configs.py:5-9), num_filters=192 "
+                         "(BASELINE configs[3])"),
+    "bb": dict(n=24, h=768, w=512, c=192, lmbda=0.01, variant="bb", metric="bb_sga R-D iters/sec (768x512, 192 filters)",
+               desc="bb_sga.py bits-back variant 24x768x512x3, num_filters=192, lambda=0.01 (BASELINE configs[4])"),
+}
+TRAFFIC_FILE = os.path.join("profiles", "r2_traffic.json")     # per-kernel DRAM bytes from the committed ncu --set full capture
+TECNICK_PER_GPU = 13                                           # ceil(100 / 8): the 8-GPU share; fewer GPUs run 13 x N images
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -53,16 +73,21 @@ def flops_per_iteration(n, h, w, c):
     return f, 2.0 * fwd
 
 
+def layer3_bytes(n, h, w, c):
+    """Algorithmic HBM bytes of the two layer-3 kernels: bf16 act_2 / s_2 / gb_2 [n,8hy,8wy,c], fp32 x,
+    bf16 gx4 [n,16hy,16wy,4]."""
+    hy, wy = -(-h // 16), -(-w // 16)
+    act = n * (8 * hy) * (8 * wy) * c * 2
+    gx4 = n * (16 * hy) * (16 * wy) * 4 * 2
+    return {"l3_fwd": act + n * h * w * 3 * 4 + gx4, "l3_dgrad": gx4 + 2 * act + act}
+
+
 def measured_traffic():
-    """DRAM bytes of the (de)conv launches of one step from the newest committed `ncu --set full` capture
-    (profiles/*_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py)."""
-    import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
-    if not files:
-        return None, None
-    with open(files[-1]) as fh:
-        d = json.load(fh)
-    return d.get("conv_dram_bytes_per_launch"), os.path.basename(files[-1])
+    p = os.path.join(ROOT, TRAFFIC_FILE)
+    if not os.path.exists(p):
+        return {}
+    with open(p) as fh:
+        return json.load(fh)
 
 
 def peaks():
@@ -71,7 +96,7 @@ def peaks():
         with open(p) as fh:
             d = json.load(fh)
         return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
-                    hbm=float(d.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+                    hbm=float(d.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json: sustained bf16, copy bandwidth)")
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
@@ -133,57 +158,51 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# the CPU arm: oracle port of the reference graph, driven like sga.py:210-215
+# the CPU arm: baseline/cpu_sga.py, the reference loop restated on PyTorch-CPU, on the workload's own batch
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps, warmup, budget_s=150.0, samples=((768, 512), (384, 256), (256, 256), (128, 128))):
-    """Returns (it/s extrapolated to the 24x768x512 batch, cores, sample description, seconds per sample step)."""
-    import torch
+def cpu_arm(wl, steps, warmup, budget_s):
+    """Times `steps` iterations of the workload's reference batch on the host cores.  The whole batch is processed every
+    iteration (same config as the GPU arm); only if the projected run would exceed `budget_s` is the batch cut to its first
+    k images and the rate scaled by k/n (stated in `sample`, same_config False)."""
     import sga_b200
-    from oracle import sga_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    W = O._to(sga_b200.weights.make_synthetic(C, 0), torch.float32)
-
-    def run(h, w, n_steps, n_warm):
-        x = torch.from_numpy(sga_b200.synth.synthetic_images(1, h, w, 0).astype(np.float32) / 255.0)
-        y, z = O.analysis(x, W)
-        opt = O.Adam(lr=0.005)
-        ts = []
-        for it in range(n_warm + n_steps):
-            t0 = time.perf_counter()
-            T = O.annealed_temperature(it, r=1e-3, ub=0.5, scheme="exp0", t0=700)
-            out = O.sga_graph(x, y, z, W, T, O.draw_noise(y, z, 0, it), LMBDA, n_ref=N_IMAGES)
-            y, z = opt.update([y, z], [out["grad_y"], out["grad_z"]])
-            _ = float(out["rd_loss"])
-            if it >= n_warm:
-                ts.append(time.perf_counter() - t0)
-        return float(np.mean(ts))
-
-    t_probe = run(128, 128, 1, 1)                       # also warms the CPU kernels
-    per_px = t_probe / (128 * 128)
-    chosen = samples[-1]
-    for (h, w) in samples:
-        if per_px * h * w * (steps + warmup) <= budget_s:
-            chosen = (h, w)
-            break
-    t = run(chosen[0], chosen[1], steps, warmup)
-    scale = (N_IMAGES * HEIGHT * WIDTH) / float(chosen[0] * chosen[1])
-    sample = ("1 image of %dx%d (1/%.0f of the 24x768x512 batch by pixels), %d timed SGA iterations; PyTorch-CPU "
-              "restatement of the reference TF1 graph (oracle/sga_oracle.py), it/s extrapolated linearly in pixels"
-              % (chosen[0], chosen[1], scale, steps))
-    return 1.0 / (t * scale), cores, sample, t
+    from baseline import cpu_sga
+    if wl["variant"] != "sga":
+        return None
+    n_batch = wl["n"] if wl["n"] <= 24 else 7                   # Tecnick: one reference batch of 7 (configs.py:8-9)
+    W = sga_b200.weights.make_synthetic(wl["c"], 0)
+    x = sga_b200.synth.synthetic_images(n_batch, wl["h"], wl["w"], 0)
+    probe = cpu_sga.run(x[:1], W, wl["lmbda"], 1, 1)            # 1 image: warms the CPU kernels and sizes the run
+    projected = probe["seconds"][0] * n_batch * (steps + warmup)
+    k = n_batch
+    if projected > budget_s:
+        k = max(1, int(n_batch * budget_s / projected))
+    r = cpu_sga.run(x[:k], W, wl["lmbda"], steps, warmup, chunk=4)
+    t = float(np.mean(r["seconds"]))
+    its = (1.0 / t) * (k / float(n_batch)) * (n_batch / float(wl["n"]))
+    sample = ("%d timed iterations (+%d warm-up) of %s%d images of %dx%d per iteration, autograd backward, host Adam, x "
+              "re-fed every iteration (baseline/cpu_sga.py: PyTorch-CPU restatement of the reference TF1 graph, %d threads, "
+              "chunks of %d images)" % (steps, warmup, "the full batch: " if k == wl["n"] else "", k, wl["h"], wl["w"],
+                                        r["cores"], r["chunk"]))
+    if k != wl["n"]:
+        sample += "; it/s scaled to the %d-image job linearly in images" % wl["n"]
+    return dict(value=its, cores=r["cores"], sample=sample, same_config=(k == wl["n"]), seconds_per_iteration=t,
+                images_per_iteration=k, rd_loss_last=r["last"]["rd_loss"])
 
 
-def main_reference(args, rank):
+def main_reference(args, rank, wl):
     if rank != 0:
         return
-    v, cores, sample, t = cpu_reference_rate(args.steps, args.warmup)
+    r = cpu_arm(wl, args.steps, args.warmup, budget_s=280.0)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for workload %s" % args.workload}), flush=True)
+        return
+    v = r["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": wl["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SGA 24x768x512x3, num_filters=192, lambda=0.01 (BASELINE configs[1])"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["desc"], "same_config": r["same_config"], "images_per_iteration": r["images_per_iteration"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -193,25 +212,59 @@ def main_reference(args, rank):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def main_ours(args, rank, ws, local):
+def rank_segments(wl, rank, ws, images_override=None):
+    """[(n_ref, first_image_in_batch, batch_index, global_lo, n_local)] of this rank (sga_b200.dist.rank_segments)."""
+    from sga_b200 import dist as D
+    if images_override:
+        return [(wl["n"] if wl["n"] <= 24 else 7, 0, 0, rank * images_override, images_override)], images_override * ws
+    total = wl["n"]
+    if wl["n"] > 24:
+        total = min(wl["n"], TECNICK_PER_GPU * ws)
+    segs = D.rank_segments(total, wl["h"] * wl["w"], rank, ws)
+    return [(s["n_ref"], s["first_in_batch"], s["batch"], s["lo"], s["hi"] - s["lo"]) for s in segs], total
+
+
+def main_ours(args, rank, ws, local, wl):
     import torch
     import torch.distributed as dist
     import sga_b200
-    from sga_b200 import dist as D
-    from sga_b200.engine import SgaEngine
+    from sga_b200.engine import BbEngine, SgaEngine
     from sga_b200.schedule import annealed_temperature
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    lo, hi = D.shard_range(N_IMAGES, rank, ws)
-    n_loc = hi - lo
-    W = sga_b200.weights.make_synthetic(C, 0)
-    imgs = sga_b200.synth.synthetic_images(N_IMAGES, HEIGHT, WIDTH, 0)[lo:hi]
-    x_host = torch.from_numpy(imgs.astype(np.float32) / 255.0).pin_memory()
-    x = x_host.to(dev)
-    eng = SgaEngine(W, n_loc, HEIGHT, WIDTH, C, LMBDA, n_ref=N_IMAGES, operand=args.operand, seed=0)
-    y0, z0 = eng.encode_init(x)
+    C, H, Wd, lmbda, bb = wl["c"], wl["h"], wl["w"], wl["lmbda"], wl["variant"] == "bb"
+    segs, total_images = rank_segments(wl, rank, ws, args.images)
+    W = sga_b200.weights.make_synthetic_bb(C, 0) if bb else sga_b200.weights.make_synthetic(C, 0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    K, Wm = args.steps, args.warmup
+    temp = lambda it: annealed_temperature(it, r=1e-3, ub=0.5, scheme="exp0", t0=700)
+
+    # one engine per segment (a contiguous image range inside ONE reference batch: n_ref and the noise offset are per batch)
+    jobs = []
+    all_imgs = sga_b200.synth.synthetic_images(total_images, H, Wd, 0) if total_images <= 24 else None
+    for (n_ref, first, batch, g_lo, n_loc) in segs:
+        if n_loc == 0:
+            continue
+        # the images of a batch do not depend on the sharding; large inputs are generated per segment (content is irrelevant)
+        imgs = all_imgs[g_lo:g_lo + n_loc] if all_imgs is not None else sga_b200.synth.synthetic_images(n_loc, H, Wd, g_lo)
+        x_host = torch.from_numpy(imgs.astype(np.float32) / 255.0).pin_memory()
+        x = x_host.to(dev)
+        Eng = BbEngine if bb else SgaEngine
+        eng = Eng(W, n_loc, H, Wd, C, lmbda, n_ref=n_ref, operand=args.operand, seed=batch, first_image=first)
+        if bb:
+            y0 = eng.encode_init(x)
+            zm0, zl0 = eng.hyper_init(y0)
+            init = (y0, zm0, zl0)
+        else:
+            init = eng.encode_init(x)
+        jobs.append(dict(eng=eng, x=x, x_host=x_host, init=init, n=n_loc))
     torch.cuda.synchronize()
+    n_loc_total = sum(j["n"] for j in jobs)
+
+    def new_state(j):
+        return j["eng"].new_state(*[t.clone() for t in j["init"]])
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,126 +279,196 @@ def main_ours(args, rank, ws, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    temp = lambda it: annealed_temperature(it, r=1e-3, ub=0.5, scheme="exp0", t0=700)
+    def run_iterations(states, first, count, rate_only=False):
+        """`count` device-resident iterations of every engine of this rank (interleaved in short segments when a rank holds
+        several reference batches, so that they advance together)."""
+        seg = count if len(jobs) == 1 else 8
+        for s0 in range(0, count, seg):
+            n = min(seg, count - s0)
+            for j, st in zip(jobs, states):
+                if bb:
+                    for k in range(n):
+                        it = first + s0 + k
+                        j["eng"].step(None if rate_only else j["x"], st, 1.0 if rate_only else temp(it), it,
+                                      0.003 if rate_only else 0.005, rate_only=rate_only, want_stats=False)
+                else:
+                    j["eng"].loop(j["x"], st, [temp(first + s0 + k) for k in range(n)], first + s0, want_stats=False)
 
-    # ---- (1) device-resident loop: `value` (un-instrumented), then the same K steps again with one CUDA event pair
-    #      around every launch on the launching stream for the roofline (the event pairs serialise the launches, i.e.
-    #      switch off the programmatic-dependent-launch overlap, so they stay out of the pass that yields `value`)
-    st = eng.new_state(y0.clone(), z0.clone())
-    for it in range(args.warmup):
-        eng.step(x, st, temp(it), it, want_stats=False)
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- (1) device-resident loop: `value`
+    states = [new_state(j) for j in jobs]
+    run_iterations(states, 0, Wm)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        it = args.warmup + k
-        eng.step(x, st, temp(it), it, want_stats=False)
-    e1.record()
-    barrier()
-    launches = eng.launch_count() - l0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
+    l0 = jobs[0]["eng"].launch_count() if jobs else 0
+    ms_total = timed(lambda: run_iterations(states, Wm, K))
+    launches = (jobs[0]["eng"].launch_count() - l0) if jobs else 0
+    ms_per_step = ms_total / K
     value = 1000.0 / ms_per_step
-    eng.profile(True)
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for k in range(args.steps):
-        it = args.warmup + args.steps + k
-        eng.step(x, st, temp(it), it, want_stats=False)
-    e3.record()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    prof = eng.profile_read()
-    eng.profile(False)
-    ms_per_step_instrumented = max_over_ranks(e2.elapsed_time(e3)) / args.steps
 
-    # ---- (2) end-to-end through the public API with host buffers
-    st2 = eng.new_state(y0.clone(), z0.clone())
-    xbuf = [torch.empty_like(x), torch.empty_like(x)]
+    # ---- (2) the same K iterations with one CUDA event pair around every launch (single stream, no graph, no PDL overlap)
+    for j in jobs:
+        j["eng"].profile(True)
+    ms_instr = timed(lambda: run_iterations(states, Wm + K, K)) / K
+    clocks = sampler.stop() if sampler else None
+    prof = {}
+    for j in jobs:
+        for k, (ms, cnt) in j["eng"].profile_read().items():
+            a = prof.setdefault(k, [0.0, 0])
+            a[0] += ms; a[1] += cnt
+        j["eng"].profile(False)
+
+    # bits-back: the second, rate-only loop (bb_sga.py:239-261) is timed separately
+    rate_loop = None
+    if bb:
+        st2 = []
+        for j, st in zip(jobs, states):
+            yt = torch.round(st["y"])
+            zm, zl = j["eng"].hyper_init(yt)
+            st2.append(j["eng"].new_state(yt, zm, zl))
+        run_iterations(st2, 0, Wm, rate_only=True)
+        ms_r = timed(lambda: run_iterations(st2, Wm, K, rate_only=True)) / K
+        rate_loop = {"value": 1000.0 / ms_r, "unit": UNIT, "ms_per_step": ms_r,
+                     "what": "rate-only loop over [z_mean, z_logvar] with y_tilde = round(y) (bb_sga.py:239-261): h_s fwd + "
+                             "dgrad and the elementwise rate kernels, no synthesis transform"}
+
+    # ---- (3) end to end through the public API, one iteration per call, x from pinned host memory every iteration
+    states2 = [new_state(j) for j in jobs]
     copy_stream = torch.cuda.Stream()
-    stats_host = torch.empty((args.steps + args.warmup, eng.n_stats), dtype=torch.float32).pin_memory()
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    for j in jobs:
+        j["xbuf"] = [torch.empty_like(j["x"]), torch.empty_like(j["x"])]
+        j["ready"] = [torch.cuda.Event(), torch.cuda.Event()]
+        j["freed"] = [torch.cuda.Event(), torch.cuda.Event()]
+        j["stats_host"] = torch.empty((K + Wm, j["eng"].n_stats), dtype=torch.float32).pin_memory()
+        for b in range(2):
+            j["freed"][b].record(stream)
 
     def e2e_steps(first, count):
-        main = torch.cuda.current_stream()
         for k in range(count):
             it = first + k
             b = k & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[b])
-                xbuf[b].copy_(x_host, non_blocking=True)          # host -> device every step (sga.py:212-214)
-                ready[b].record(copy_stream)
-            main.wait_event(ready[b])
-            eng.step(xbuf[b], st2, temp(it), it, want_stats=True)
-            freed[b].record(main)
-            stats_host[it].copy_(eng.stats, non_blocking=True)    # device -> host read of the step's statistics
-        torch.cuda.current_stream().synchronize()
+            for j, st in zip(jobs, states2):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(j["freed"][b])
+                    j["xbuf"][b].copy_(j["x_host"], non_blocking=True)      # host -> device every iteration (sga.py:212-214)
+                    j["ready"][b].record(copy_stream)
+                stream.wait_event(j["ready"][b])
+                if bb:
+                    j["eng"].step(j["xbuf"][b], st, temp(it), it, 0.005, want_stats=True)
+                else:
+                    j["eng"].loop(j["xbuf"][b], st, [temp(it)], it, want_stats=True)
+                j["freed"][b].record(stream)
+                j["stats_host"][it].copy_(j["eng"].stats, non_blocking=True)   # device -> host read of the statistics
+        stream.synchronize()
 
-    for b in range(2):
-        freed[b].record(torch.cuda.current_stream())
-    e2e_steps(0, args.warmup)
-    barrier()
-    e0.record()
-    e2e_steps(args.warmup, args.steps)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    last = eng.unpack_stats(stats_host[args.warmup + args.steps - 1].numpy())
-    if not (np.isfinite(stats_host.numpy()).all()):
-        raise RuntimeError("non-finite SGA statistics inside the timed loop (rd_loss %r): the measurement is void" % last["rd_loss"])
+    e2e_steps(0, Wm)
+    e2e_ms = timed(lambda: e2e_steps(Wm, K)) / K
+    last = None
+    for j in jobs:
+        if not np.isfinite(j["stats_host"].numpy()).all():
+            raise RuntimeError("non-finite SGA statistics inside the timed loop: the measurement is void")
+        last = j["eng"].unpack_stats(j["stats_host"][Wm + K - 1].numpy())
+    h2d = sum(int(j["x_host"].numel()) * 4 for j in jobs)
+    d2h = sum(int(j["eng"].n_stats) * 4 for j in jobs)
+    ws_bytes = sum(j["eng"].workspace_bytes for j in jobs)
+    if ws > 1:
+        t = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
 
     if rank != 0:
         return
-    fl, flops_iter = flops_per_iteration(n_loc, HEIGHT, WIDTH, C)
+    # ---- accounting (rank 0's shard; every rank runs the same kernels on its own images)
     pk = peaks()
+    fl, flops_iter = {}, 0.0
+    l3b = {"l3_fwd": 0.0, "l3_dgrad": 0.0}
+    for j in jobs:
+        f, tot = flops_per_iteration(j["n"], H, Wd, C)
+        for k, v in f.items():
+            fl[k] = fl.get(k, 0.0) + v
+        flops_iter += tot
+        for k, v in layer3_bytes(j["n"], H, Wd, C).items():
+            l3b[k] += v
+    fused = C in (64, 128, 192)
     conv_labels = {"hs0_fwd": "hs0", "hs1_fwd": "hs1", "hs2_fwd": "hs2", "hs0_dgrad": "hs0", "hs1_dgrad": "hs1",
                    "hs2_dgrad": "hs2", "gs0_fwd": "gs0", "gs1_fwd": "gs1", "gs2_fwd": "gs2", "gs0_dgrad": "gs0",
                    "gs1_dgrad": "gs1", "gs2_dgrad": "gs2"}
-    # algorithmic FLOPs executed inside each (de)conv launch: the conv itself plus the IGDN channel mixing fused into it
-    # (forward: IGDN_i after conv_i; backward: IGDN_{i-1} in the dgrad of conv_i; IGDN_2's backward is in k_l3_dgrad_igdn)
-    fused_extra = {"gs0_fwd": "igdn0", "gs1_fwd": "igdn1", "gs2_fwd": "igdn2", "gs1_dgrad": "igdn0", "gs2_dgrad": "igdn1"}
-    kfl = {k: fl[conv_labels[k]] + (fl[fused_extra[k]] if (k in fused_extra and C in (64, 128, 192)) else 0.0)
-           for k in conv_labels}
-    conv_ms = sum(prof[k][0] for k in conv_labels if k in prof)
-    conv_fl = sum(kfl[k] * prof[k][1] for k in conv_labels if k in prof)
-    conv_launches = sum(prof[k][1] for k in conv_labels if k in prof)
-    achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    traffic, traffic_src = measured_traffic()
-    if traffic is not None and ws > 1:
-        traffic = traffic / ws          # the capture is of the 24-image job on one GPU
-    breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}
-    per_layer = {k: round(kfl[k] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12, 1) for k in conv_labels
-                 if k in prof and prof[k][0] > 0}
+    # algorithmic FLOPs executed inside each launch group: the conv plus the IGDN channel mixing fused into it (forward:
+    # IGDN_i after conv_i; backward: IGDN_{i-1} in the dgrad of conv_i, IGDN_2 in the layer-3 dgrad)
+    fused_extra = {"gs0_fwd": "igdn0", "gs1_fwd": "igdn1", "gs2_fwd": "igdn2", "gs1_dgrad": "igdn0", "gs2_dgrad": "igdn1",
+                   "l3_dgrad": "igdn2"}
+    kfl = {k: fl[v] for k, v in conv_labels.items()}
+    kfl["l3_fwd"] = fl["gs3"]
+    kfl["l3_dgrad"] = fl["gs3"]
+    if fused:
+        for k, v in fused_extra.items():
+            kfl[k] += fl[v]
+    else:
+        kfl["igdn_fwd"] = sum(fl["igdn%d" % i] for i in range(3))
+        kfl["igdn_bwd"] = kfl["igdn_fwd"]
+    traffic = measured_traffic()
+    kernels = {}
+    for k, (ms, cnt) in sorted(prof.items()):
+        ms_it = ms / K                                  # this launch group's time per iteration (all engines of the rank)
+        row = {"ms_per_step": round(ms_it, 4), "launches_per_step": cnt / float(K)}
+        if k in ("l3_fwd", "l3_dgrad"):
+            ach = l3b[k] / (ms_it * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4),
+                       tflops=round(kfl[k] / (ms_it * 1e-3) / 1e12, 1))
+        elif k in kfl:
+            ach = kfl[k] / (ms_it * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4))
+        if traffic.get("workload") == args.workload and k in traffic.get("kernels", {}) and not args.images:
+            row["traffic"] = traffic["kernels"][k] * (n_loc_total / float(wl["n"]))     # captured on the whole batch on one GPU
+        kernels[k] = row
+    dom = "gs2_fwd"
+    dom_row = kernels.get(dom, {})
+    tensor_ms = sum(v[0] for k, v in prof.items() if k in kfl) / K
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16" if args.operand == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "SGA 24x768x512x3, num_filters=192, lambda=0.01 (BASELINE configs[1])",
-                   "images_per_gpu": n_loc, "operand": args.operand + " operands, fp32 accumulate (TMEM); latents/Adam fp32",
-                   "cache": "inputs larger than L2 (activations %.1f GB per step)" % (eng.workspace_bytes / 1e9),
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if wl["n"] <= 24 else "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.operand == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "images_total": total_images, "images_per_gpu": n_loc_total,
+                   "engines_per_gpu": len(jobs),
+                   "operand": args.operand + " operands, fp32 accumulate (TMEM); latents/Adam fp32",
+                   "cache": "inputs larger than L2 (%.1f GB of activations rewritten every step)" % (ws_bytes / 1e9),
+                   "loop": "sga_loop: CUDA graph of the two-stream step replayed; x resident" if not bb
+                           else "sga_bb_step per iteration (eager launches)",
                    "final_step": {"rd_loss": last["rd_loss"], "train_bpp": last["train_bpp"], "train_mse": last["train_mse"]}},
-        "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 * ws),
-                "d2h_bytes_per_step": int(eng.n_stats * 4 * ws), "ms_per_step": e2e_ms},
+        "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
-                     "kernel": "tcgen05 implicit-GEMM (de)conv kernels: k_conv_tc x9 + k_conv_igdn_fwd x3 per step",
-                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean over the 12 launches, 24 images)",
-                     "traffic_source": traffic_src, "peak_source": pk["source"], "launches_timed": conv_launches,
-                     "timed": "second pass of the same K steps with a CUDA event pair around every launch (%.3f ms/step; "
-                              "the value pass is un-instrumented)" % ms_per_step_instrumented,
-                     "per_layer_tflops": per_layer,
-                     "whole_step_tflops": flops_iter * value / 1e12,
-                     "whole_step_frac": flops_iter * value / 1e12 / pk["tflops"]},
-        "ms_per_step_by_kernel": breakdown,
+                     "kernel": ("k_conv_igdn_fwd<%d,2> (g_s layer 2 forward: transposed 5x5 conv + fused inverse GDN), the step's "
+                                "largest launch" % C) if fused else "k_conv_tc (g_s layer 2 forward, un-fused)",
+                     "achieved": dom_row.get("achieved"), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": dom_row.get("frac"),
+                     "traffic": dom_row.get("traffic"),
+                     "traffic_source": TRAFFIC_FILE if dom_row.get("traffic") is not None else None,
+                     "peak_source": pk["source"],
+                     "timed": "third pass: the same K iterations with a CUDA event pair around every launch on the launching "
+                              "stream, single stream, no graph (%.3f ms/step; the value pass is un-instrumented)" % ms_instr,
+                     "whole_step": {"gflop_per_iteration": round(flops_iter / 1e9, 1),
+                                    "tflops": round(flops_iter * value / 1e12 / 1.0, 1) if ws == 1 else None,
+                                    "frac_of_tensor_peak": round(flops_iter * 1000.0 / ms_per_step / 1e12 / pk["tflops"], 4),
+                                    "tensor_kernels_ms": round(tensor_ms, 4)},
+                     "kernels": kernels},
         "clocks": clocks,
     }
+    if rate_loop:
+        line["rate_loop"] = rate_loop
     if ws == 1 and not args.no_cpu:
-        v, cores, sample, _ = cpu_reference_rate(2, 1, budget_s=40.0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        r = cpu_arm(wl, 2, 1, budget_s=45.0)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "same_config": r["same_config"]}
     print(json.dumps(line), flush=True)
 
 
@@ -355,15 +478,19 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kodak192", choices=sorted(WORKLOADS))
     ap.add_argument("--operand", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--images", type=int, default=0, help="diagnostic: images per GPU (e.g. 3 = the 8-GPU shard on one GPU); "
+                                                          "not a BASELINE configuration")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        main_reference(args, rank)
+        main_reference(args, rank, wl)
         return
     import __graft_entry__ as ge
     if rank == 0 or not os.path.exists(os.path.join(ge.PKG, "libsga_b200.so")):
@@ -375,7 +502,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
-    main_ours(args, rank, ws, local)
+    main_ours(args, rank, ws, local, wl)
     if ws > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -47,7 +47,7 @@ PROF_NAMES = {0: "elementwise", 1: "igdn_fwd", 2: "igdn_bwd", 3: "l3_fwd", 4: "l
 # every symbol include/sga_b200.h declares
 EXPORTS = [
     "sga_last_error", "sga_version", "sga_create", "sga_destroy", "sga_workspace_bytes", "sga_latent_shape",
-    "sga_bind_weights", "sga_encode_init", "sga_grad", "sga_step", "sga_eval_hard", "sga_reconstruction",
+    "sga_bind_weights", "sga_encode_init", "sga_grad", "sga_step", "sga_loop", "sga_eval_hard", "sga_reconstruction",
     "sga_launch_count", "sga_profile_enable", "sga_profile_read", "sga_op_soft_round",
     "sga_op_eb_likelihood", "sga_op_gauss_likelihood", "sga_op_adam", "sga_op_conv", "sga_op_gdn", "sga_op_igdn_bwd",
     "sga_bb_hyper_init", "sga_bb_grad", "sga_bb_step", "sga_bb_eval",
@@ -83,6 +83,7 @@ def load():
     lib.sga_encode_init.argtypes = [vp, vp, vp, vp, vp]
     lib.sga_grad.argtypes = [vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     lib.sga_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp]
+    lib.sga_loop.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(f32), i32, i32, vp, vp]
     lib.sga_eval_hard.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.sga_reconstruction.argtypes = [vp, vp, vp]
     lib.sga_launch_count.restype = ctypes.c_longlong

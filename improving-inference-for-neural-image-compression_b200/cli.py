@@ -65,6 +65,7 @@ def compress(args, out=print):
     from . import weights as Wm
     from .engine import EVAL_FIELDS, SgaEngine
     from .msssim import msssim_per_image
+    from .schedule import annealed_temperature
 
     rank, ws, local = D.init_process_group()
     if torch.cuda.is_available():
@@ -76,51 +77,79 @@ def compress(args, out=print):
         args.lmbda = float(args.runname.split("lmbda=")[1].split("-")[0])
         say("Defaulting lmbda (mse coefficient) to %g as used in model training." % args.lmbda)
     W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, args.num_filters)
-    results = {k: [] for k in EVAL_FIELDS}
-    engines = {}
-    for (b_lo, b_hi) in D.reference_batches(num_images, H * Wd):
-        n_ref = b_hi - b_lo
-        lo, hi = D.shard_range(n_ref, rank, ws)
-        n_loc = hi - lo
+    batches = D.reference_batches(num_images, H * Wd)
+    # This rank's images: a contiguous global range cut at the reference's batch boundaries.  Every segment is one engine
+    # with its batch's n_ref; the Philox key is the batch index and the counter offset the position inside the batch, so
+    # every image of the input gets its own noise whatever the sharding (the reference's TF stream also keeps advancing
+    # from batch to batch).  All segments advance together, so a many-batch input keeps every GPU busy with all of its
+    # images at once instead of walking the batches one after the other.
+    segs = D.rank_segments(num_images, H * Wd, rank, ws)
+    jobs = []
+    for sg in segs:
+        eng = SgaEngine(W, sg["hi"] - sg["lo"], H, Wd, args.num_filters, args.lmbda, n_ref=sg["n_ref"], operand=args.operand,
+                        seed=sg["batch"], first_image=sg["first_in_batch"])
+        x = torch.from_numpy(X[sg["lo"]:sg["hi"]].astype(np.float32) / 255.0).cuda()                 # sga.py:52-53
+        y, z = eng.encode_init(x)                                                                    # sga.py:207
+        jobs.append(dict(seg=sg, eng=eng, x=x, st=eng.new_state(y, z)))
+    its = args.sga_its
+    temps = [annealed_temperature(it, r=args.annealing_rate, ub=0.5, scheme="exp0", t0=args.t0) for it in range(its)]
+    log_points = [it for it in range(its) if it % 100 == 0 or it + 1 == its]                          # sga.py:216
+    nb = len(batches)
+    nf = 7 if args.verbose else 4
+    lines = [[] for _ in batches]
+    t_loop = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] if torch.cuda.is_available() else None
+    if t_loop:
+        torch.cuda.synchronize()
+        t_loop[0].record()
+    first = 0
+    for end in log_points:
+        for j in jobs:                                         # device-resident segment [first, end] of the loop (sga.py:210-215)
+            j["eng"].loop(j["x"], j["st"], temps[first:end + 1], first, want_stats=True)
+        acc = np.zeros((nb, nf))
+        for j in jobs:
+            s = j["eng"].unpack_stats(j["eng"].stats.cpu().numpy())
+            row = [s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())]
+            if args.verbose:                                   # sga.py:218-230: the same statistics with hard-rounded latents
+                ex = j["eng"].eval_hard(j["x"], j["st"]["y"], j["st"]["z"])
+                row += [ex["rd_loss"], ex["train_bpp"], float(ex["psnr"].sum())]
+            acc[j["seg"]["batch"]] += row
+        tot = np.asarray(D.allreduce_scalars(acc.reshape(-1).tolist())).reshape(nb, nf)
+        for b, (b_lo, b_hi) in enumerate(batches):
+            line = "it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (end, temps[end], tot[b, 0], tot[b, 1], tot[b, 2],
+                                                                              tot[b, 3] / (b_hi - b_lo))
+            if args.verbose:
+                line += "\t after rounding: rd_loss=%.4f, bpp=%.4f psnr=%.4f" % (tot[b, 4], tot[b, 5], tot[b, 6] / (b_hi - b_lo))
+            if not np.isfinite(tot[b]).all():
+                raise FloatingPointError("non-finite SGA statistics at iteration %d of batch %d: %s" % (end, b, line))
+            lines[b].append(line)
+        first = end + 1
+    loop_ms = None
+    if t_loop:
+        t_loop[1].record()
+        torch.cuda.synchronize()
+        loop_ms = t_loop[0].elapsed_time(t_loop[1])
+    for b in range(nb):                                        # the reference's output, batch after batch
         say("----RD Optimization----")                        # sga.py:206
-        rows = np.zeros((0, 7), dtype=np.float32)
-        eng = None
-        if n_loc > 0:
-            if n_loc not in engines or engines[n_loc][1] != (n_ref, lo):
-                if n_loc in engines:
-                    engines[n_loc][0].close()
-                engines[n_loc] = (SgaEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref,
-                                            operand=args.operand, seed=0, first_image=lo), (n_ref, lo))
-            eng = engines[n_loc][0]
-            x = torch.from_numpy(X[b_lo + lo:b_lo + hi].astype(np.float32) / 255.0).cuda()       # sga.py:52-53
-        def log(it, T, s, extra):
-            tot = D.allreduce_scalars([s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())]
-                                      + ([extra["rd_loss"], extra["train_bpp"], float(extra["psnr"].sum())] if extra else []))
-            line = "it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (it, T, tot[0], tot[1], tot[2], tot[3] / n_ref)
-            if extra:                                         # sga.py:218-230 (--verbose)
-                line += "\t after rounding: rd_loss=%.4f, bpp=%.4f psnr=%.4f" % (tot[4], tot[5], tot[6] / n_ref)
+        for line in lines[b]:
             say(line)
-        if eng is not None:
-            y, z, ev = eng.run(x, its=args.sga_its, annealing_rate=args.annealing_rate, t0=args.t0, log=log,
-                               verbose=args.verbose)
-            ms = msssim_per_image(eng.reconstruction(), x)
-            rows = np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
-                             ev["est_y_bpp"], ev["est_z_bpp"]], axis=1).astype(np.float32)
-        elif ws > 1:
-            # ranks without images still take part in the log-point all-reduces
-            from .schedule import annealed_temperature
-            for it in range(args.sga_its):
-                if it % 100 == 0 or it + 1 == args.sga_its:
-                    D.allreduce_scalars([0.0] * (7 if args.verbose else 4))
         say()
-        full = D.gather_rows(rows, n_ref, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
-        for i, k in enumerate(EVAL_FIELDS):
-            results[k] += full[:, i].tolist()
-    for e, _ in engines.values():
-        e.close()
+    rows = []
+    for j in jobs:                                             # sga.py:240-247
+        ev = j["eng"].eval_hard(j["x"], j["st"]["y"], j["st"]["z"])
+        ms = msssim_per_image(j["eng"].reconstruction(), j["x"])
+        rows.append(np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
+                              ev["est_y_bpp"], ev["est_z_bpp"]], axis=1).astype(np.float32))
+        j["eng"].close()
+    rows = np.concatenate(rows, axis=0) if rows else np.zeros((0, 7), dtype=np.float32)
+    full = D.gather_rows(rows, num_images, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
+    if loop_ms is not None and its > 0:
+        loop_ms = max(D.allgather_floats(loop_ms))
+        say("SGA loop: %d iterations of %d images (%d reference batch%s) on %d GPU%s in %.2f s = %.1f it/s"
+            % (its, num_images, nb, "" if nb == 1 else "es", ws, "" if ws == 1 else "s", loop_ms / 1000.0,
+               its / (loop_ms / 1000.0)))
     if rank != 0:
         return None
-    results = {k: np.asarray(v) for k, v in results.items()}
+    results = {k: np.asarray(full[:, i]) for i, k in enumerate(EVAL_FIELDS)}
     input_file = os.path.basename(args.input_file)
     trained_script_name = args.runname.split("-")[0]
     save_file = "rd-%s-input=%s.npz" % (args.runname, input_file)

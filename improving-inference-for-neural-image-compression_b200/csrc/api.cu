@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tc_kernels.h"
@@ -28,6 +29,7 @@ struct ConvW {
   bf16* wb_fwd = nullptr;   // [tap][cout][cin] K-major B operand
   bf16* wb_dgrad = nullptr; // [tap][cin][cout]
   float* bias = nullptr;
+  int fwd_dup = 1;          // wb_fwd holds the weights fwd_dup times along K (hi|lo split input operand)
 };
 
 // bits-back variant (bb_sga.py): how z_tilde is produced and which part of the graph is evaluated
@@ -80,6 +82,26 @@ struct sga_ctx {
   IgdnTc *ig_f[3] = {0, 0, 0}, *ig_b[3] = {0, 0, 0};
   L3Tc* l3 = nullptr;
   bool fused = false;   // IGDN runs inside the (de)conv epilogues (num_filters in {64,128,192})
+  int split0 = 0;       // y_tilde / z_tilde enter g_s / h_s layer 0 as hi|lo bf16 pairs (K = 2C), see store_operand_pair
+
+  // two-stream schedule + graph replay (sga_loop)
+  cudaStream_t side = nullptr, main = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_soft = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
+  static constexpr int kSpCap = 1024;      // iterations per upload of the step-parameter table
+  StepParams* sp_table = nullptr;          // device
+  int* sp_idx = nullptr;                   // device counter, advanced by the last kernel of a replayed step
+  StepParams* sp_host = nullptr;           // pinned staging, 2 x kSpCap
+  cudaEvent_t ev_sp[2] = {nullptr, nullptr};
+  int sp_half = 0;
+  float* stats_dev = nullptr;
+  struct GraphKey { const void *x, *y, *z, *my, *vy, *mz, *vz; };
+  struct GraphRec { GraphKey key; cudaGraphExec_t exec; long long kernels; };
+  std::vector<GraphRec> graphs;
+
+  // one arena for the activations: the fp32 set (init, final eval, fp32 steps) and the bf16 set (the loop) are never live
+  // at the same time -- every step / evaluation rewrites all of its activations -- so they overlap
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
 
   // event-based per-kernel timing (sga_profile_*)
   bool prof = false;
@@ -177,8 +199,9 @@ static int igdn_bwd_f32(const float* g, const float* x, const float* s, const fl
   return launch_igdn_bwd_finish(g, x, s, u, n, gx, st);
 }
 
+// dup_fwd = 2: the forward operand of this layer is a hi|lo split tensor with 2*cin channels (weights stacked twice)
 static int bind_conv(sga_ctx* c, ConvW& w, const float* kernel, const float* bias, int kh, int kw, int cin, int cout,
-                     bool need_bf16, cudaStream_t st) {
+                     bool need_bf16, cudaStream_t st, int dup_fwd = 1) {
   w.kh = kh; w.kw = kw; w.cin = cin; w.cout = cout;
   const long long n = static_cast<long long>(kh) * kw * cin * cout;
   SGA_TRY(c->alloc(&w.w, n));
@@ -190,9 +213,10 @@ static int bind_conv(sga_ctx* c, ConvW& w, const float* kernel, const float* bia
     SGA_CUDA(cudaMemcpyAsync(w.bias, bias, cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   if (need_bf16) {
-    SGA_TRY(c->alloc(&w.wb_fwd, n));
+    SGA_TRY(c->alloc(&w.wb_fwd, n * dup_fwd));
     SGA_TRY(c->alloc(&w.wb_dgrad, n));
-    SGA_TRY(launch_pack_weights_bf16(w.w, kh * kw, cin, cout, false, w.wb_fwd, st));
+    w.fwd_dup = dup_fwd;
+    SGA_TRY(launch_pack_weights_bf16(w.w, kh * kw, cin, cout, false, w.wb_fwd, st, dup_fwd));
     SGA_TRY(launch_pack_weights_bf16(w.w, kh * kw, cin, cout, true, w.wb_dgrad, st));
   }
   return SGA_OK;
@@ -201,7 +225,8 @@ static int bind_conv(sga_ctx* c, ConvW& w, const float* kernel, const float* bia
 static int make_tc(int kind, const ConvW& w, int N, int Hin, int Win, const bf16* x, TcConv** out, int fuse = 0,
                    const bf16* mix_op = nullptr) {
   ConvPlan plan;
-  SGA_TRY(make_conv_plan(kind, w.kh, w.kw, N, Hin, Win, w.cin, w.cout, &plan));
+  const bool fwd_kind = (kind == kUp2 || kind == kS1True);
+  SGA_TRY(make_conv_plan(kind, w.kh, w.kw, N, Hin, Win, fwd_kind ? w.cin * w.fwd_dup : w.cin, w.cout, &plan));
   return tc_conv_create(plan, x, plan.w_transposed ? w.wb_dgrad : w.wb_fwd, fuse, mix_op, out);
 }
 
@@ -351,14 +376,133 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
   return SGA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The bf16 iteration of sga.py:211-215 as a two-stream schedule.  The synthesis chain (94 % of the FLOPs) only needs
+// y_tilde, so it starts right after the soft round of y; the hyper path (z soft round + prior rate -> h_s -> Gaussian rate
+// of y -> h_s dgrads -> Adam on z) runs beside it on the context's side stream and joins before Adam on y:
+//
+//   main : memset acc . fork . y_soft .(ev_soft). gs0 gs1 gs2 fwd . l3 fwd . l3 dgrad . gs2 gs1 gs0 dgrad . join . adam(y) . stats
+//   side :               z_path hs0 hs1 hs2 fwd . wait(ev_soft) . y_rate . hs2 hs1 hs0 dgrad . adam(z)
+//
+// The same function is what sga_loop captures into a CUDA graph (spt / spi: temperature, noise step and lr_t then come
+// from the device table).  With per-launch profiling on, everything is issued on the one stream so that the event pairs
+// bracket single kernels.
+// ---------------------------------------------------------------------------------------------------
+struct StepOut {
+  float *y, *z, *m_y, *v_y, *m_z, *v_z;   // in-place Adam update (sga_step / sga_loop) ...
+  float *grad_y, *grad_z;                 // ... or the gradients only (sga_grad)
+};
+
+static int step_bf16(sga_ctx* c, const float* x, const float* y, const float* z, float T, int step, const float* ny,
+                     const float* nz, float* stats, cudaStream_t st, const StepOut& o, const StepParams* spt = nullptr,
+                     const int* spi = nullptr, int* spi_adv = nullptr) {
+  const Dims& d = c->d;
+  const sga_config& g = c->cfg;
+  const float rate_scale = static_cast<float>(1.0 / (log(2.0) * d.H * static_cast<double>(d.W) * g.n_ref));
+  const bool two = !c->prof && c->side != nullptr && getenv("SGA_ONE_STREAM") == nullptr;
+  cudaStream_t s2 = two ? c->side : st;
+  const long long off_y = g.first_image * (d.ny / d.N), off_z = g.first_image * (d.nz / d.N);
+  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 5 * d.N * sizeof(double), st));
+  if (two) {
+    SGA_CUDA(cudaEventRecord(c->ev_fork, st));
+    SGA_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+  }
+  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_y_soft(y, ny, d.ny, d.C, T, g.clip_eps, g.seed, step, c->f_yt, c->b_yt, c->dy, off_y,
+                                                  st, spt, spi, c->split0));
+  if (two) SGA_CUDA(cudaEventRecord(c->ev_soft, st));
+  // ---- hyper path, forward
+  PROF(c, SGA_PROF_ELEMENTWISE, s2, launch_z_path<bf16>(z, nz, d.nz, d.nz / d.N, d.C, c->eb_pack, T, g.clip_eps, g.seed, step, 0,
+                                                        rate_scale, c->b_zt, c->gz_rate, c->dz, c->acc + d.N, off_z, s2, spt, spi,
+                                                        c->split0));
+  PROF(c, SGA_PROF_CONV_HS + 0, s2, tc_conv_launch(c->tc_hs[0], c->hs[0].bias, 1, nullptr, c->b_h0, nullptr, s2));
+  PROF(c, SGA_PROF_CONV_HS + 1, s2, tc_conv_launch(c->tc_hs[1], c->hs[1].bias, 1, nullptr, c->b_h1, nullptr, s2));
+  PROF(c, SGA_PROF_CONV_HS + 2, s2, tc_conv_launch(c->tc_hs[2], c->hs[2].bias, 0, nullptr, nullptr, c->h2, s2));
+  // ---- synthesis path, forward (main stream)
+  for (int i = 0; i < 3; ++i) {
+    if (c->fused) {
+      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch_igdn_fwd(c->tc_gs[i], c->gs[i].bias, c->gs_beta[i], c->b_s[i],
+                                                                c->b_act[i], st));
+    } else {
+      PROF(c, SGA_PROF_CONV_GS + i, st, tc_conv_launch(c->tc_gs[i], c->gs[i].bias, 0, nullptr, c->b_xpre[i], nullptr, st));
+      PROF(c, SGA_PROF_IGDN_FWD, st, igdn_tc_forward(c->ig_f[i], c->b_xpre[i], c->gs_beta[i], c->b_act[i], c->b_s[i], st));
+    }
+  }
+  // ---- rate of y and the hyper path's backward (side stream)
+  if (two) SGA_CUDA(cudaStreamWaitEvent(s2, c->ev_soft, 0));
+  PROF(c, SGA_PROF_ELEMENTWISE, s2, launch_y_path<bf16>(nullptr, nullptr, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, T, g.clip_eps,
+                                                        g.seed, step, 0, rate_scale, nullptr, c->gy_rate, nullptr, c->b_gh2,
+                                                        c->acc, off_y, s2, c->f_yt));
+  PROF(c, SGA_PROF_CONV_HS + 5, s2, tc_conv_launch(c->tc_hs_d[2], nullptr, 0, c->b_h1, c->b_gh1, nullptr, s2));
+  PROF(c, SGA_PROF_CONV_HS + 4, s2, tc_conv_launch(c->tc_hs_d[1], nullptr, 0, c->b_h0, c->b_gh0, nullptr, s2));
+  PROF(c, SGA_PROF_CONV_HS + 3, s2, tc_conv_launch(c->tc_hs_d[0], nullptr, 0, nullptr, nullptr, c->gz_hyper, s2));
+  if (o.z != nullptr) {
+    PROF(c, SGA_PROF_ELEMENTWISE, s2, launch_adam(o.z, o.m_z, o.v_z, c->gz_rate, c->gz_hyper, c->dz, d.nz, g.lr, g.beta1, g.beta2,
+                                                  g.adam_eps, step, nullptr, s2, spt, spi));
+  } else if (o.grad_z != nullptr) {
+    SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gz_rate, c->gz_hyper, c->dz, d.nz, g.lr, g.beta1, g.beta2, g.adam_eps, 0,
+                        o.grad_z, s2));
+  }
+  if (two) SGA_CUDA(cudaEventRecord(c->ev_join, s2));
+  // ---- distortion and the synthesis path's backward (main stream)
+  const float grad_scale =
+      (g.lmbda > 0.0f) ? static_cast<float>(2.0 * 65025.0 * g.lmbda / (static_cast<double>(g.n_ref) * d.H * d.W * 3.0))
+                       : 0.0f;
+  PROF(c, SGA_PROF_L3_FWD, st, l3_tc_forward(c->l3, c->gs3_bias_host, x, grad_scale, nullptr, c->b_gx4, c->acc + 2 * d.N,
+                                             c->acc + 3 * d.N, st));
+  if (g.lmbda > 0.0f) {
+    if (c->fused) {
+      // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
+      // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
+      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
+      PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
+      PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
+      PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
+    } else {
+      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
+      for (int i = 2; i >= 0; --i) {
+        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[i], c->b_ga[i], c->b_xpre[i], c->b_s[i], c->b_gb[i], st));
+        if (i == 0) PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
+        else PROF(c, SGA_PROF_CONV_GS + 3 + i, st, tc_conv_launch(c->tc_gs_d[i], nullptr, 0, nullptr, c->b_ga[i - 1], nullptr, st));
+      }
+    }
+  } else {
+    SGA_CUDA(cudaMemsetAsync(c->gy_dist, 0, d.ny * sizeof(float), st));
+  }
+  if (two) SGA_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  if (o.y != nullptr) {
+    PROF(c, SGA_PROF_ELEMENTWISE, st, launch_adam(o.y, o.m_y, o.v_y, c->gy_rate, c->gy_dist, c->dy, d.ny, g.lr, g.beta1, g.beta2,
+                                                  g.adam_eps, step, nullptr, st, spt, spi));
+  } else if (o.grad_y != nullptr) {
+    SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gy_rate, c->gy_dist, c->dy, d.ny, g.lr, g.beta1, g.beta2, g.adam_eps, 0,
+                        o.grad_y, st));
+  }
+  if (stats != nullptr || spi_adv != nullptr)
+    PROF(c, SGA_PROF_ELEMENTWISE, st, launch_finalize_stats(c->acc, d.N, g.n_ref, d.H, d.W, g.lmbda,
+                                                            stats ? stats : c->stats_dev, st, spi_adv));
+  return SGA_OK;
+}
+
 static int grad_common(sga_ctx* c, const float* x, const float* y, const float* z, float T, int step, const float* ny,
-                       const float* nz, float* stats, cudaStream_t st) {
+                       const float* nz, float* stats, cudaStream_t st, const StepOut& o) {
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
   SGA_CHECK(T > 0.0f, "temperature must be positive");
   SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are driven through sga_bb_grad / sga_bb_step");
-  if (c->cfg.operand == SGA_OPERAND_BF16) return forward_backward_bf16(c, x, y, z, T, step, ny, nz, stats, st);
+  if (c->cfg.operand == SGA_OPERAND_BF16) return step_bf16(c, x, y, z, T, step, ny, nz, stats, st, o);
   SGA_TRY(forward_f32(c, x, y, z, T, step, ny, nz, 0, true, stats, st));
-  return backward_f32(c, st);
+  SGA_TRY(backward_f32(c, st));
+  const sga_config& g = c->cfg;
+  if (o.y != nullptr) {
+    SGA_TRY(launch_adam(o.y, o.m_y, o.v_y, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1, g.beta2, g.adam_eps, step,
+                        nullptr, st));
+    SGA_TRY(launch_adam(o.z, o.m_z, o.v_z, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1, g.beta2, g.adam_eps, step,
+                        nullptr, st));
+  } else {
+    SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1, g.beta2, g.adam_eps,
+                        0, o.grad_y, st));
+    SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1, g.beta2, g.adam_eps,
+                        0, o.grad_z, st));
+  }
+  return SGA_OK;
 }
 
 }  // namespace sga
@@ -393,32 +537,72 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
   const long long nh2 = static_cast<long long>(d.N) * d.Hh * d.Wh * 2 * d.C;
   const long long nxt = static_cast<long long>(d.N) * d.Hs[4] * d.Ws[4] * 3;
   const long long e3 = gs_elems(d, 3);
+  const bool bf = (cfg->operand == SGA_OPERAND_BF16);
+  c->fused = bf && tc_conv_can_fuse(d.C) && getenv("SGA_NO_FUSE") == nullptr;
+  {
+    const char* es = getenv("SGA_SPLIT0");
+    c->split0 = (bf && cfg->variant == SGA_VARIANT_SGA && !(es != nullptr && es[0] == '0')) ? 1 : 0;
+  }
+  // ---- live across phases
   A(&c->acc, 5 * d.N);
   if (cfg->variant == SGA_VARIANT_BITS_BACK) A(&c->bb_ha, 2 * d.nz);
   A(&c->dz, d.nz); A(&c->gz_rate, d.nz); A(&c->gz_hyper, d.nz);
   A(&c->dy, d.ny); A(&c->gy_rate, d.ny); A(&c->gy_dist, d.ny);
   A(&c->h2, nh2);
-  // fp32 forward (init / eval / fp32 steps)
-  A(&c->f_zt, d.nz); A(&c->f_h0, nh0); A(&c->f_h1, nh1); A(&c->f_yt, d.ny); A(&c->f_gh2, nh2);
-  for (int i = 0; i < 3; ++i) { A(&c->f_xpre[i], gs_elems(d, i + 1)); A(&c->f_s[i], gs_elems(d, i + 1)); A(&c->f_act[i], gs_elems(d, i + 1)); }
-  A(&c->f_xt, nxt); A(&c->f_gx, nxt);
+  A(&c->f_yt, d.ny);                       // fp32 y_tilde: input of the fp32 forward and of the bf16 loop's rate kernel
+  A(&c->stats_dev, SGA_STATS_HEADER + 6 * d.N);
+  A(&c->sp_table, sga_ctx::kSpCap); A(&c->sp_idx, 1);
+  // ---- the two overlapping activation sets: two passes over the same list, first sizing, then carving
   const long long ninit = static_cast<long long>(d.N) * d.Hg[1] * d.Wg[1] * d.C;
   const long long nscratch = e3 > ninit ? e3 : ninit;
-  A(&c->f_tmp, nscratch); A(&c->f_nrm, nscratch);
-  A(&c->f_init[0], ninit); A(&c->f_init[1], ninit);
-  for (int i = 0; i < 3; ++i) { c->f_ga[i] = nullptr; c->f_gb[i] = nullptr; }
+  for (int i = 0; i < 3; ++i) { c->f_ga[i] = nullptr; c->f_gb[i] = nullptr; c->b_xpre[i] = nullptr; c->b_ga[i] = nullptr; }
   c->f_gh1 = c->f_gh0 = nullptr;
-  if (cfg->operand == SGA_OPERAND_F32) {
-    for (int i = 0; i < 3; ++i) { A(&c->f_ga[i], gs_elems(d, i + 1)); A(&c->f_gb[i], gs_elems(d, i + 1)); }
-    A(&c->f_gh1, nh1); A(&c->f_gh0, nh0);
-  } else {
-    A(&c->b_zt, d.nz); A(&c->b_h0, nh0); A(&c->b_h1, nh1); A(&c->b_yt, d.ny); A(&c->b_gh2, nh2);
-    for (int i = 0; i < 3; ++i) {
-      A(&c->b_xpre[i], gs_elems(d, i + 1)); A(&c->b_s[i], gs_elems(d, i + 1)); A(&c->b_act[i], gs_elems(d, i + 1));
-      A(&c->b_ga[i], gs_elems(d, i + 1)); A(&c->b_gb[i], gs_elems(d, i + 1));
+  for (int pass = 0; pass < 2 && st == SGA_OK; ++pass) {
+    size_t off = 0;
+    auto R = [&](auto** p, long long n) {
+      typedef typename std::remove_pointer<typename std::remove_pointer<decltype(p)>::type>::type T;
+      const size_t nb = ((static_cast<size_t>(n > 0 ? n : 1) * sizeof(T)) + 1023u) & ~static_cast<size_t>(1023u);
+      if (pass == 1) *p = reinterpret_cast<T*>(c->arena + off);
+      off += nb;
+    };
+    // fp32 set
+    R(&c->f_zt, d.nz); R(&c->f_h0, nh0); R(&c->f_h1, nh1); R(&c->f_gh2, nh2);
+    for (int i = 0; i < 3; ++i) { R(&c->f_xpre[i], gs_elems(d, i + 1)); R(&c->f_s[i], gs_elems(d, i + 1)); R(&c->f_act[i], gs_elems(d, i + 1)); }
+    R(&c->f_xt, nxt); R(&c->f_gx, nxt);
+    R(&c->f_tmp, nscratch); R(&c->f_nrm, nscratch);
+    R(&c->f_init[0], ninit); R(&c->f_init[1], ninit);
+    if (!bf) {
+      for (int i = 0; i < 3; ++i) { R(&c->f_ga[i], gs_elems(d, i + 1)); R(&c->f_gb[i], gs_elems(d, i + 1)); }
+      R(&c->f_gh1, nh1); R(&c->f_gh0, nh0);
     }
-    A(&c->b_gx4, static_cast<long long>(d.N) * d.Hs[4] * d.Ws[4] * 4);
-    A(&c->b_gh1, nh1); A(&c->b_gh0, nh0);
+    const size_t f32_bytes = off;
+    off = 0;
+    if (bf) {
+      const int dup = c->split0 ? 2 : 1;
+      R(&c->b_zt, dup * d.nz); R(&c->b_h0, nh0); R(&c->b_h1, nh1); R(&c->b_yt, dup * d.ny); R(&c->b_gh2, nh2);
+      for (int i = 0; i < 3; ++i) {
+        R(&c->b_s[i], gs_elems(d, i + 1)); R(&c->b_act[i], gs_elems(d, i + 1)); R(&c->b_gb[i], gs_elems(d, i + 1));
+        if (!c->fused) { R(&c->b_xpre[i], gs_elems(d, i + 1)); R(&c->b_ga[i], gs_elems(d, i + 1)); }
+      }
+      R(&c->b_gx4, static_cast<long long>(d.N) * d.Hs[4] * d.Ws[4] * 4);
+      R(&c->b_gh1, nh1); R(&c->b_gh0, nh0);
+    }
+    if (pass == 0) {
+      c->arena_bytes = f32_bytes > off ? f32_bytes : off;
+      A(&c->arena, static_cast<long long>(c->arena_bytes));
+    }
+  }
+  if (st == SGA_OK && bf) {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_soft, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    for (int h = 0; h < 2 && e == cudaSuccess; ++h) e = cudaEventCreateWithFlags(&c->ev_sp[h], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->sp_host, 2 * sga_ctx::kSpCap * sizeof(StepParams));
+    if (e != cudaSuccess) { set_error("stream / event setup failed: %s", cudaGetErrorString(e)); st = SGA_ERR_CUDA; }
   }
   if (st != SGA_OK) { sga_destroy(c); return st; }
   *out = c;
@@ -432,6 +616,11 @@ int sga_destroy(sga_ctx* c) {
     igdn_tc_destroy(c->ig_f[i]); igdn_tc_destroy(c->ig_b[i]);
   }
   l3_tc_destroy(c->l3);
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->main) cudaStreamDestroy(c->main);
+  for (cudaEvent_t e : {c->ev_fork, c->ev_soft, c->ev_join, c->ev_in, c->ev_out, c->ev_sp[0], c->ev_sp[1]}) if (e) cudaEventDestroy(e);
+  if (c->sp_host) cudaFreeHost(c->sp_host);
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
@@ -460,12 +649,13 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
   const int ga_ci[4] = {3, C, C, C};
   for (int i = 0; i < 4; ++i) SGA_TRY(bind_conv(c, c->ga[i], w->ga_kernel[i], w->ga_bias[i], 5, 5, ga_ci[i], C, false, st));
   const int gs_co[4] = {C, C, C, 3};
-  for (int i = 0; i < 4; ++i) SGA_TRY(bind_conv(c, c->gs[i], w->gs_kernel[i], w->gs_bias[i], 5, 5, C, gs_co[i], bf && i < 3, st));
+  for (int i = 0; i < 4; ++i)
+    SGA_TRY(bind_conv(c, c->gs[i], w->gs_kernel[i], w->gs_bias[i], 5, 5, C, gs_co[i], bf && i < 3, st, (i == 0 && c->split0) ? 2 : 1));
   SGA_TRY(bind_conv(c, c->ha[0], w->ha_kernel[0], w->ha_bias[0], 3, 3, C, C, false, st));
   SGA_TRY(bind_conv(c, c->ha[1], w->ha_kernel[1], w->ha_bias[1], 5, 5, C, C, false, st));
   // bits-back variant: h_a emits 2C channels, z_mean | z_logvar (bb_sga.py:69,99)
   SGA_TRY(bind_conv(c, c->ha[2], w->ha_kernel[2], nullptr, 5, 5, C, c->cfg.variant == SGA_VARIANT_BITS_BACK ? 2 * C : C, false, st));
-  SGA_TRY(bind_conv(c, c->hs[0], w->hs_kernel[0], w->hs_bias[0], 5, 5, C, C, bf, st));
+  SGA_TRY(bind_conv(c, c->hs[0], w->hs_kernel[0], w->hs_bias[0], 5, 5, C, C, bf, st, c->split0 ? 2 : 1));
   SGA_TRY(bind_conv(c, c->hs[1], w->hs_kernel[1], w->hs_bias[1], 5, 5, C, d.mid, bf, st));
   SGA_TRY(bind_conv(c, c->hs[2], w->hs_kernel[2], w->hs_bias[2], 3, 3, d.mid, 2 * C, bf, st));
   for (int i = 0; i < 3; ++i) {
@@ -493,7 +683,6 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
     SGA_TRY(make_tc(kS1TrueDgrad, c->hs[2], d.N, d.Hh, d.Wh, c->b_gh2, &c->tc_hs_d[2]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[1], d.N, d.Hh, d.Wh, c->b_gh1, &c->tc_hs_d[1]));
     SGA_TRY(make_tc(kUp2Dgrad, c->hs[0], d.N, 2 * d.Hz, 2 * d.Wz, c->b_gh0, &c->tc_hs_d[0]));
-    c->fused = tc_conv_can_fuse(C) && getenv("SGA_NO_FUSE") == nullptr;
     for (int i = 0; i < 3; ++i) {
       const bf16* in = (i == 0) ? c->b_yt : c->b_act[i - 1];
       const long long pix = static_cast<long long>(d.N) * d.Hs[i + 1] * d.Ws[i + 1];
@@ -621,25 +810,90 @@ int sga_bb_eval(sga_ctx* c, const float* x, const float* y_tilde, const float* z
 
 int sga_grad(sga_ctx* c, const float* x, const float* y, const float* z, float T, int32_t step, const float* ny,
              const float* nz, float* grad_y, float* grad_z, float* stats, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SGA_TRY(grad_common(c, x, y, z, T, step, ny, nz, stats, st));
-  const sga_config& g = c->cfg;
-  SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1, g.beta2,
-                      g.adam_eps, 0, grad_y, st));
-  SGA_TRY(launch_adam(nullptr, nullptr, nullptr, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1, g.beta2,
-                      g.adam_eps, 0, grad_z, st));
-  return SGA_OK;
+  SGA_CHECK(grad_y != nullptr && grad_z != nullptr, "null gradient output");
+  const StepOut o{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, grad_y, grad_z};
+  return grad_common(c, x, y, z, T, step, ny, nz, stats, static_cast<cudaStream_t>(stream), o);
 }
 
 int sga_step(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* v_y, float* m_z, float* v_z, float T,
              int32_t step, const float* ny, const float* nz, float* stats, void* stream) {
+  SGA_CHECK(y && z && m_y && v_y && m_z && v_z, "null state tensor");
+  const StepOut o{y, z, m_y, v_y, m_z, v_z, nullptr, nullptr};
+  return grad_common(c, x, y, z, T, step, ny, nz, stats, static_cast<cudaStream_t>(stream), o);
+}
+
+// n_steps iterations of sga.py:210-215 without host work per iteration: the step is captured once into a CUDA graph
+// (both streams, programmatic dependent launches included) and replayed; temperature / noise step / Adam lr_t of
+// iteration k come from a device table indexed by a device counter that the step's last kernel advances.
+int sga_loop(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* v_y, float* m_z, float* v_z,
+             const float* temperatures, int32_t first_step, int32_t n_steps, float* stats, void* stream) {
+  SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are driven through sga_bb_step");
+  SGA_CHECK(x && y && z && m_y && v_y && m_z && v_z && temperatures, "null argument");
+  SGA_CHECK(n_steps >= 0 && first_step >= 0, "bad step range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SGA_TRY(grad_common(c, x, y, z, T, step, ny, nz, stats, st));
   const sga_config& g = c->cfg;
-  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_adam(y, m_y, v_y, c->gy_rate, c->gy_dist, c->dy, c->d.ny, g.lr, g.beta1,
-                                                g.beta2, g.adam_eps, step, nullptr, st));
-  PROF(c, SGA_PROF_ELEMENTWISE, st, launch_adam(z, m_z, v_z, c->gz_rate, c->gz_hyper, c->dz, c->d.nz, g.lr, g.beta1,
-                                                g.beta2, g.adam_eps, step, nullptr, st));
+  for (int k = 0; k < n_steps; ++k) SGA_CHECK(temperatures[k] > 0.0f, "temperature must be positive");
+  const StepOut o{y, z, m_y, v_y, m_z, v_z, nullptr, nullptr};
+  const bool graphed = c->cfg.operand == SGA_OPERAND_BF16 && !c->prof && getenv("SGA_NO_GRAPH") == nullptr;
+  if (graphed && (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)) {
+    // the default streams cannot be captured: run on the context's own stream, ordered after / before the caller's
+    SGA_CUDA(cudaEventRecord(c->ev_in, st));
+    SGA_CUDA(cudaStreamWaitEvent(c->main, c->ev_in, 0));
+    const int rc = sga_loop(c, x, y, z, m_y, v_y, m_z, v_z, temperatures, first_step, n_steps, stats, c->main);
+    SGA_CUDA(cudaEventRecord(c->ev_out, c->main));
+    SGA_CUDA(cudaStreamWaitEvent(st, c->ev_out, 0));
+    return rc;
+  }
+  if (!graphed) {
+    // fp32 contexts (cross-check arithmetic) and per-launch profiling: plain launches
+    for (int k = 0; k < n_steps; ++k)
+      SGA_TRY(grad_common(c, x, y, z, temperatures[k], first_step + k, nullptr, nullptr, (k + 1 == n_steps) ? stats : nullptr, st, o));
+    return SGA_OK;
+  }
+  // the captured step (keyed by the tensors it is bound to)
+  const sga_ctx::GraphKey key{x, y, z, m_y, v_y, m_z, v_z};
+  sga_ctx::GraphRec* rec = nullptr;
+  for (auto& r : c->graphs)
+    if (memcmp(&r.key, &key, sizeof(key)) == 0) rec = &r;
+  if (rec == nullptr && n_steps > 0) {
+    if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+    cudaGraph_t graph = nullptr;
+    const long long l0 = g_launches;
+    SGA_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = step_bf16(c, x, y, z, 1.0f, 0, nullptr, nullptr, c->stats_dev, st, o, c->sp_table, c->sp_idx, c->sp_idx);
+    const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+    const long long kernels = g_launches - l0;
+    g_launches = l0;
+    if (rc != SGA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ec != cudaSuccess) { set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(ec)); return SGA_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); return SGA_ERR_CUDA; }
+    c->graphs.push_back(sga_ctx::GraphRec{key, exec, kernels});
+    rec = &c->graphs.back();
+  }
+  for (int done = 0; done < n_steps;) {
+    const int n = (n_steps - done < sga_ctx::kSpCap) ? n_steps - done : sga_ctx::kSpCap;
+    const int h = c->sp_half;
+    c->sp_half ^= 1;
+    SGA_CUDA(cudaEventSynchronize(c->ev_sp[h]));          // the previous upload from this half of the staging buffer is done
+    StepParams* hp = c->sp_host + h * sga_ctx::kSpCap;
+    for (int k = 0; k < n; ++k) {
+      const int it = first_step + done + k;
+      hp[k] = StepParams{temperatures[done + k], static_cast<float>(adam_lr_t(g.lr, g.beta1, g.beta2, it)), it, 0};
+    }
+    SGA_CUDA(cudaMemcpyAsync(c->sp_table, hp, n * sizeof(StepParams), cudaMemcpyHostToDevice, st));
+    SGA_CUDA(cudaEventRecord(c->ev_sp[h], st));
+    SGA_CUDA(cudaMemsetAsync(c->sp_idx, 0, sizeof(int), st));
+    for (int k = 0; k < n; ++k) SGA_CUDA(cudaGraphLaunch(rec->exec, st));
+    g_launches += rec->kernels * n;
+    done += n;
+  }
+  if (stats != nullptr && n_steps > 0)
+    SGA_CUDA(cudaMemcpyAsync(stats, c->stats_dev, (SGA_STATS_HEADER + SGA_STATS_PER_IMAGE * c->d.N) * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
   return SGA_OK;
 }
 

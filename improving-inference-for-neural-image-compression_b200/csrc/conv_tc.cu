@@ -716,27 +716,30 @@ int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* act_saved, con
   return launch_tc(c, P, st);
 }
 
-__global__ void k_pack_weights(const float* __restrict__ w, int taps, int Cin, int Cout, int transposed,
+__global__ void k_pack_weights(const float* __restrict__ w, int taps, int Cin, int Cout, int transposed, int dup,
                                __nv_bfloat16* __restrict__ o) {
-  // forward kinds: o[t][n=co][k=ci] = w[t][ci][co]; dgrads: o[t][n=ci][k=co] = w[t][ci][co]
+  // forward kinds: o[t][n=co][k] = w[t][k % Cin][co] for k < dup*Cin (dup = 2: the hi|lo split operand of the first layers
+  // sees the same weights twice); dgrads: o[t][n=ci][k=co] = w[t][ci][co]
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(taps) * Cin * Cout;
+  const long long total = static_cast<long long>(taps) * Cin * Cout * dup;
   if (e >= total) return;
   if (transposed) {
     o[e] = __float2bfloat16_rn(w[e]);
   } else {
-    const int k = static_cast<int>(e % Cin);
-    const long long r = e / Cin;
+    const int K = Cin * dup;
+    const int k = static_cast<int>(e % K);
+    const long long r = e / K;
     const int n = static_cast<int>(r % Cout);
     const int t = static_cast<int>(r / Cout);
-    o[e] = __float2bfloat16_rn(w[(static_cast<long long>(t) * Cin + k) * Cout + n]);
+    o[e] = __float2bfloat16_rn(w[(static_cast<long long>(t) * Cin + (k % Cin)) * Cout + n]);
   }
 }
 
 int launch_pack_weights_bf16(const float* w_ref, int taps, int Cin, int Cout, bool transposed, __nv_bfloat16* out,
-                             cudaStream_t st) {
-  const long long total = static_cast<long long>(taps) * Cin * Cout;
-  k_pack_weights<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w_ref, taps, Cin, Cout, transposed ? 1 : 0,
+                             cudaStream_t st, int dup) {
+  if (transposed) dup = 1;
+  const long long total = static_cast<long long>(taps) * Cin * Cout * dup;
+  k_pack_weights<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w_ref, taps, Cin, Cout, transposed ? 1 : 0, dup,
                                                                               out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;

@@ -90,6 +90,36 @@ __device__ __forceinline__ float soft_round_fast(float v, float u0, float u1, fl
   *dvt = (c - f) * s1 * s0 * dl * invT * invT;
   return f * s0 + c * s1;
 }
+// Graph-replayed loop (sga_loop): temperature, noise step and Adam's lr_t come from a device table indexed by a device
+// counter, so that one captured step can be replayed for every iteration without the host touching it.
+__device__ __forceinline__ void step_override(const StepParams* __restrict__ spt, const int* __restrict__ spi, float& T,
+                                              int& step) {
+  if (spt != nullptr) {
+    const StepParams sp = spt[*spi];
+    T = sp.T;
+    step = sp.step;
+  }
+}
+
+// operand store of a soft-rounded pair (c, c+1) of pixel `pix`: plain [pix][C], or -- split -- [pix][2C] with the bf16
+// value in [0,C) and the bf16 of its rounding residual in [C,2C); the first layer then runs with K = 2C against the
+// weights stacked twice, so that it sees v_tilde to ~16 mantissa bits (|y| >= 64 would otherwise lose the fraction
+// that SGA optimises: bf16 spacing 0.5)
+__device__ __forceinline__ void store_operand_pair(float* base, long long pix, int C, int c, float a, float b, int split) {
+  *reinterpret_cast<float2*>(base + pix * C + c) = make_float2(a, b);
+}
+__device__ __forceinline__ void store_operand_pair(__nv_bfloat16* base, long long pix, int C, int c, float a, float b,
+                                                   int split) {
+  const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+  if (!split) {
+    *reinterpret_cast<__nv_bfloat162*>(base + pix * C + c) = hi;
+  } else {
+    *reinterpret_cast<__nv_bfloat162*>(base + pix * 2 * C + c) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(base + pix * 2 * C + C + c) =
+        __floats2bfloat162_rn(a - __low2float(hi), b - __high2float(hi));
+  }
+}
+
 template <bool FAST>
 __device__ __forceinline__ float soft_round_sel(float v, float u0, float u1, float T, float eps, float* dvt) {
   return FAST ? soft_round_fast(v, u0, u1, T, eps, dvt) : soft_round_one(v, u0, u1, T, eps, dvt);
@@ -240,12 +270,14 @@ __global__ void k_eb_pack(const float* m0, const float* m1, const float* m2, con
 //   dz     : d z_tilde / d z                                      bits[n] += -ln p  (double)
 // hard != 0: z_tilde = rint(z) (sga.py:240-241), no noise.
 // ------------------------------------------------------------------------------------------------
-template <typename AT>
+template <typename AT, bool FAST = std::is_same<AT, __nv_bfloat16>::value>
 __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ inj, long long numel,
                          long long per_image, int C, const float* __restrict__ pk, float T, float eps, uint64_t seed,
                          int step, int hard, float rate_scale, AT* __restrict__ zt_act, float* __restrict__ g_rate,
-                         float* __restrict__ dz, double* __restrict__ bits, long long ctr_off) {
+                         float* __restrict__ dz, double* __restrict__ bits, long long ctr_off,
+                         const StepParams* __restrict__ spt, const int* __restrict__ spi, int split) {
   ew_pdl_begin();
+  step_override(spt, spi, T, step);
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long e0 = pair * 2;
   float nll = 0.0f;
@@ -254,24 +286,28 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
     img = e0 / per_image;
     float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
     if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Z, u, ctr_off);
+    float ztk[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const long long e = e0 + k;
       if (e < numel) {
         float d = 0.0f, zt;
         if (hard) zt = rintf(z[e]);
-        else zt = soft_round_sel<std::is_same<AT, __nv_bfloat16>::value>(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
+        else zt = soft_round_sel<FAST>(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
         EbParams P;
         eb_load(pk, C, static_cast<int>(e % C), P);
         float dp;
         const float p = eb_likelihood_one(P, zt, &dp);
         const float pc = fmaxf(p, 1e-9f);
         nll += -logf(pc);
-        zt_act[e] = from_f32<AT>(zt);
+        ztk[k] = zt;
         if (g_rate) g_rate[e] = (-rate_scale / pc) * dp;
         if (dz) dz[e] = d;
       }
     }
+    // C is even and e0 is even: the pair (e0, e0 + 1) lies in one pixel
+    if (e0 + 1 < numel) store_operand_pair(zt_act, e0 / C, C, static_cast<int>(e0 % C), ztk[0], ztk[1], split);
+    else zt_act[e0] = from_f32<AT>(ztk[0]);
   }
   // per-image reduction: a warp may straddle an image boundary only if per_image is not a multiple of 64
   const unsigned full = 0xffffffffu;
@@ -505,7 +541,8 @@ template <typename AT, bool FAST = std::is_same<AT, __nv_bfloat16>::value>
 __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ inj, const float* __restrict__ h2,
                          int N, int Hy, int Wy, int Hh, int Wh, int C, float T, float eps, uint64_t seed, int step,
                          int hard, float rate_scale, AT* __restrict__ yt_act, float* __restrict__ g_rate,
-                         float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits, long long ctr_off) {
+                         float* __restrict__ dy, AT* __restrict__ g_h2, double* __restrict__ bits, long long ctr_off,
+                         const float* __restrict__ yt_in) {
   ew_pdl_begin();
   const int halfC = C >> 1;
   const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -526,9 +563,10 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
       const long long numel = static_cast<long long>(N) * Hy * Wy * C;
       const long long e0 = ((static_cast<long long>(n) * Hy + i) * Wy + j) * C + c;
       float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-      if (!hard) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u, ctr_off);
+      if (!hard && yt_in == nullptr) pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u, ctr_off);
       // the pair (c, c+1) is contiguous in every tensor and c is even: 8-byte / 4-byte vector accesses
-      const float2 yv = *reinterpret_cast<const float2*>(y + e0);
+      // yt_in: y_tilde was produced by k_y_soft (two-stream schedule): only the rate terms are evaluated here
+      const float2 yv = *reinterpret_cast<const float2*>((yt_in ? yt_in : y) + e0);
       const float2 muv = *reinterpret_cast<const float2*>(h2 + hpix * 2 * C + c);
       const float2 lsv = *reinterpret_cast<const float2*>(h2 + hpix * 2 * C + C + c);
       const float yk[2] = {yv.x, yv.y}, muk[2] = {muv.x, muv.y}, lsk[2] = {lsv.x, lsv.y};
@@ -536,7 +574,8 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         float d = 0.0f, yt;
-        if (hard) yt = rintf(yk[k]);
+        if (yt_in) yt = yk[k];
+        else if (hard) yt = rintf(yk[k]);
         else yt = soft_round_sel<FAST>(yk[k], u[2 * k], u[2 * k + 1], T, eps, &d);
         float dpdy, dpdsb, sigma;
         const float p = FAST ? gauss_likelihood_fast(yt, muk[k], lsk[k], &dpdy, &dpdsb, &sigma)
@@ -549,10 +588,10 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
         const float gsig = (sigma >= 0.11f || gsb < 0.0f) ? gsb : 0.0f;
         ytk[k] = yt; grk[k] = gp * dpdy; dk[k] = d; gmu[k] = -gp * dpdy; gls[k] = gsig * sigma;
       }
-      store_pair(yt_act + e0, ytk[0], ytk[1]);
+      if (yt_in == nullptr) store_pair(yt_act + e0, ytk[0], ytk[1]);
       if (g_rate) {
         *reinterpret_cast<float2*>(g_rate + e0) = make_float2(grk[0], grk[1]);
-        *reinterpret_cast<float2*>(dy + e0) = make_float2(dk[0], dk[1]);
+        if (yt_in == nullptr) *reinterpret_cast<float2*>(dy + e0) = make_float2(dk[0], dk[1]);
         store_pair(g_h2 + hpix * 2 * C + c, gmu[0], gmu[1]);
         store_pair(g_h2 + hpix * 2 * C + C + c, gls[0], gls[1]);
       }
@@ -570,6 +609,30 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
   } else if (img >= 0) {
     atomicAdd(bits + img, static_cast<double>(nll));
   }
+}
+
+// K1(y) alone (two-stream schedule of the bf16 loop): the synthesis chain only needs y_tilde, so the soft round runs
+// first on the main stream while z_path -> h_s -> rate (k_y_path with yt_in) run on the side stream.
+//   yt_f32 : y_tilde in fp32 for the rate kernel      yt_act : GEMM operand of g_s layer 0 (plain or hi|lo split)
+template <bool FAST>
+__global__ void k_y_soft(const float* __restrict__ y, const float* __restrict__ inj, long long numel, int C, float T,
+                         float eps, uint64_t seed, int step, float* __restrict__ yt_f32, __nv_bfloat16* __restrict__ yt_act,
+                         float* __restrict__ dy, long long ctr_off, const StepParams* __restrict__ spt,
+                         const int* __restrict__ spi, int split) {
+  ew_pdl_begin();
+  step_override(spt, spi, T, step);
+  const long long pair = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long e0 = pair * 2;
+  if (e0 >= numel) return;             // numel = N*Hy*Wy*C is even (C is even)
+  float u[4];
+  pair_uniforms(inj, numel, e0, seed, step, TENSOR_ID_Y, u, ctr_off);
+  const float2 yv = *reinterpret_cast<const float2*>(y + e0);
+  float d0, d1;
+  const float t0 = soft_round_sel<FAST>(yv.x, u[0], u[1], T, eps, &d0);
+  const float t1 = soft_round_sel<FAST>(yv.y, u[2], u[3], T, eps, &d1);
+  *reinterpret_cast<float2*>(yt_f32 + e0) = make_float2(t0, t1);
+  *reinterpret_cast<float2*>(dy + e0) = make_float2(d0, d1);
+  store_operand_pair(yt_act, e0 / C, C, static_cast<int>(e0 % C), t0, t1, split);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,8 +687,9 @@ __global__ void k_distortion(const float* __restrict__ x, const float* __restric
 
 // stats_out (sga_b200.h): rd_loss, train_mse, train_bpp, then per image psnr, y_bpp, z_bpp, sse, mse_rounded
 __global__ void k_finalize_stats(const double* __restrict__ acc, int N, int n_ref, int H, int W, float lmbda,
-                                 float* __restrict__ out) {
+                                 float* __restrict__ out, int* __restrict__ spi_advance) {
   ew_pdl_begin();
+  if (spi_advance != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *spi_advance += 1;   // last kernel of a replayed step
   // acc: [0,N) y nats, [N,2N) z nats, [2N,3N) sse, [3N,4N) sse rounded
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double npix = static_cast<double>(H) * W;
@@ -655,8 +719,10 @@ __global__ void k_finalize_stats(const double* __restrict__ acc, int N, int n_re
 // ------------------------------------------------------------------------------------------------
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
                        const float* __restrict__ gb, const float* __restrict__ fac, long long numel, float lr_t,
-                       float b1, float omb1, float b2, float omb2, float eps, float* __restrict__ g_out) {
+                       float b1, float omb1, float b2, float omb2, float eps, float* __restrict__ g_out,
+                       const StepParams* __restrict__ spt, const int* __restrict__ spi) {
   ew_pdl_begin();
+  if (spt != nullptr) lr_t = spt[*spi].lr_t;
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (e >= numel) return;
   float g = ga[e];
@@ -685,8 +751,10 @@ __device__ __forceinline__ float adam_one(float g, float& p, float& m, float& v,
 }
 __global__ void k_adam_v4(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ ga,
                           const float* __restrict__ gb, const float* __restrict__ fac, long long numel4, float lr_t, float b1,
-                          float omb1, float b2, float omb2, float eps) {
+                          float omb1, float b2, float omb2, float eps, const StepParams* __restrict__ spt,
+                          const int* __restrict__ spi) {
   ew_pdl_begin();
+  if (spt != nullptr) lr_t = spt[*spi].lr_t;
   const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (q >= numel4) return;
   float4 g4 = reinterpret_cast<const float4*>(ga)[q];
@@ -745,6 +813,9 @@ __global__ void k_convert(const TI* __restrict__ in, long long n, TO* __restrict
 // host launchers
 // ------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(long long n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+// SGA_EW_EXACT=1: the bf16 loop's elementwise kernels use the reference formulas (expf / logf / atanhf / divisions)
+// instead of the SFU-intrinsic variants
+static bool ew_exact() { const char* e = getenv("SGA_EW_EXACT"); return e != nullptr && e[0] == '1'; }
 
 int launch_soft_round(const float* v, const float* inj, long long numel, float T, float eps, uint64_t seed, int step,
                       int tensor_id, float* vt, float* dvt, cudaStream_t st) {
@@ -781,30 +852,50 @@ int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, l
 template <typename AT>
 int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
-                  float* dz, double* bits, long long ctr_off, cudaStream_t st) {
+                  float* dz, double* bits, long long ctr_off, cudaStream_t st, const StepParams* spt, const int* spi,
+                  int split) {
   const long long pairs = (numel + 1) / 2;
+  if (ew_exact())
+    return launch_ew(k_z_path<AT, false>, blocks_for(pairs, 256), 256, st, z, inj, numel, per_image, C, pk, T, eps, seed, step,
+                     hard, rate_scale, zt_act, g_rate, dz, bits, ctr_off, spt, spi, split);
   return launch_ew(k_z_path<AT>, blocks_for(pairs, 256), 256, st, z, inj, numel, per_image, C, pk, T, eps, seed, step, hard,
-                   rate_scale, zt_act, g_rate, dz, bits, ctr_off);
+                   rate_scale, zt_act, g_rate, dz, bits, ctr_off, spt, spi, split);
 }
 template int launch_z_path<float>(const float*, const float*, long long, long long, int, const float*, float, float,
-                                  uint64_t, int, int, float, float*, float*, float*, double*, long long, cudaStream_t);
+                                  uint64_t, int, int, float, float*, float*, float*, double*, long long, cudaStream_t,
+                                  const StepParams*, const int*, int);
 template int launch_z_path<__nv_bfloat16>(const float*, const float*, long long, long long, int, const float*, float,
                                           float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*, double*,
-                                          long long, cudaStream_t);
+                                          long long, cudaStream_t, const StepParams*, const int*, int);
 
 template <typename AT>
 int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
-                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st) {
+                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st, const float* yt_in) {
   const long long pairs = static_cast<long long>(N) * Hh * Wh * (C / 2);
+  if (ew_exact())
+    return launch_ew(k_y_path<AT, false>, blocks_for(pairs, 256), 256, st, y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step,
+                     hard, rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off, yt_in);
   return launch_ew(k_y_path<AT>, blocks_for(pairs, 256), 256, st, y, inj, h2, N, Hy, Wy, Hh, Wh, C, T, eps, seed, step, hard,
-                   rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off);
+                   rate_scale, yt_act, g_rate, dy, g_h2, bits, ctr_off, yt_in);
 }
 template int launch_y_path<float>(const float*, const float*, const float*, int, int, int, int, int, int, float, float,
-                                  uint64_t, int, int, float, float*, float*, float*, float*, double*, long long, cudaStream_t);
+                                  uint64_t, int, int, float, float*, float*, float*, float*, double*, long long, cudaStream_t,
+                                  const float*);
 template int launch_y_path<__nv_bfloat16>(const float*, const float*, const float*, int, int, int, int, int, int, float,
                                           float, uint64_t, int, int, float, __nv_bfloat16*, float*, float*,
-                                          __nv_bfloat16*, double*, long long, cudaStream_t);
+                                          __nv_bfloat16*, double*, long long, cudaStream_t, const float*);
+
+int launch_y_soft(const float* y, const float* inj, long long numel, int C, float T, float eps, uint64_t seed, int step,
+                  float* yt_f32, __nv_bfloat16* yt_act, float* dy, long long ctr_off, cudaStream_t st, const StepParams* spt,
+                  const int* spi, int split) {
+  const long long pairs = numel / 2;
+  if (ew_exact())
+    return launch_ew(k_y_soft<false>, blocks_for(pairs, 256), 256, st, y, inj, numel, C, T, eps, seed, step, yt_f32, yt_act, dy,
+                     ctr_off, spt, spi, split);
+  return launch_ew(k_y_soft<true>, blocks_for(pairs, 256), 256, st, y, inj, numel, C, T, eps, seed, step, yt_f32, yt_act, dy,
+                   ctr_off, spt, spi, split);
+}
 
 int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
                       double* sse, double* sse_r, cudaStream_t st) {
@@ -846,28 +937,35 @@ int launch_finalize_stats_bb(const double* acc, int N, int n_ref, int H, int W, 
   return launch_ew(k_finalize_stats_bb, 1, 32, st, acc, N, n_ref, H, W, lmbda, rate_only, out);
 }
 
-int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st) {
-  return launch_ew(k_finalize_stats, 1, 32, st, acc, N, n_ref, H, W, lmbda, out);
+int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st,
+                          int* spi_advance) {
+  return launch_ew(k_finalize_stats, 1, 32, st, acc, N, n_ref, H, W, lmbda, out, spi_advance);
+}
+
+double adam_lr_t(double lr, double beta1, double beta2, int iterations) {
+  const double t = iterations + 1.0;
+  return lr * (sqrt(1.0 - pow(beta2, t)) / (1.0 - pow(beta1, t)));  // adam.py:40-42 (float64 scalar)
 }
 
 int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, const float* fac, long long numel,
-                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st) {
+                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st,
+                const StepParams* spt, const int* spi) {
   if (numel <= 0) return SGA_OK;
-  const double t = iterations + 1.0;
-  const double lr_t = lr * (sqrt(1.0 - pow(beta2, t)) / (1.0 - pow(beta1, t)));  // adam.py:40-42 (float64 scalar)
+  const double lr_t = adam_lr_t(lr, beta1, beta2, iterations);
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const float f_lr = static_cast<float>(lr_t), f_b1 = static_cast<float>(beta1), f_omb1 = static_cast<float>(1.0 - beta1),
               f_b2 = static_cast<float>(beta2), f_omb2 = static_cast<float>(1.0 - beta2), f_eps = static_cast<float>(eps);
   long long done = 0;
   if (p != nullptr && g_out == nullptr && numel >= 4 && al16(p) && al16(m) && al16(v) && al16(ga) && al16(gb) && al16(fac)) {
     const long long n4 = numel / 4;
-    SGA_TRY(launch_ew(k_adam_v4, blocks_for(n4, 256), 256, st, p, m, v, ga, gb, fac, n4, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps));
+    SGA_TRY(launch_ew(k_adam_v4, blocks_for(n4, 256), 256, st, p, m, v, ga, gb, fac, n4, f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps,
+                      spt, spi));
     done = n4 * 4;
   }
   if (done < numel) {   // tail (or everything: unaligned buffers, gradient-only calls)
     SGA_TRY(launch_ew(k_adam, blocks_for(numel - done, 256), 256, st, p ? p + done : nullptr, m ? m + done : nullptr,
                       v ? v + done : nullptr, ga + done, gb ? gb + done : nullptr, fac ? fac + done : nullptr, numel - done,
-                      f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps, g_out ? g_out + done : nullptr));
+                      f_lr, f_b1, f_omb1, f_b2, f_omb2, f_eps, g_out ? g_out + done : nullptr, spt, spi));
   }
   return SGA_OK;
 }

@@ -8,6 +8,10 @@ constexpr int TENSOR_ID_Y = 1;  // Philox counter word 2 (oracle/sga_oracle.py T
 constexpr int TENSOR_ID_Z = 2;
 constexpr int TENSOR_ID_EPS = 3;  // bits-back variant: the Gaussian noise of z_tilde (oracle/bb_oracle.py)
 
+// Per-iteration scalars of the graph-replayed loop (sga_loop): a device table indexed by a device counter that the last
+// kernel of every step advances.
+struct StepParams { float T; float lr_t; int step; int pad; };
+
 // ---- elementwise.cu
 int launch_soft_round(const float* v, const float* inj, long long numel, float T, float eps, uint64_t seed, int step,
                       int tensor_id, float* vt, float* dvt, cudaStream_t st);
@@ -19,11 +23,17 @@ int launch_gauss_likelihood(const float* yt, const float* mu, const float* ls, l
 template <typename AT>
 int launch_z_path(const float* z, const float* inj, long long numel, long long per_image, int C, const float* pk,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* zt_act, float* g_rate,
-                  float* dz, double* bits, long long ctr_off, cudaStream_t st);
+                  float* dz, double* bits, long long ctr_off, cudaStream_t st, const StepParams* spt = nullptr,
+                  const int* spi = nullptr, int split = 0);
+// yt_in != nullptr: y_tilde (fp32) was produced by launch_y_soft; only the rate terms are evaluated
 template <typename AT>
 int launch_y_path(const float* y, const float* inj, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C,
                   float T, float eps, uint64_t seed, int step, int hard, float rate_scale, AT* yt_act, float* g_rate,
-                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st);
+                  float* dy, AT* g_h2, double* bits, long long ctr_off, cudaStream_t st, const float* yt_in = nullptr);
+// soft round of y alone: fp32 y_tilde, d y_tilde / d y and the bf16 operand of g_s layer 0 (split: [pix][hi C | lo C])
+int launch_y_soft(const float* y, const float* inj, long long numel, int C, float T, float eps, uint64_t seed, int step,
+                  float* yt_f32, __nv_bfloat16* yt_act, float* dy, long long ctr_off, cudaStream_t st,
+                  const StepParams* spt = nullptr, const int* spi = nullptr, int split = 0);
 // bits-back variant (bb_sga.py): z_tilde = eps*exp(logvar/2) + mean, prior density + slope, log q; see elementwise.cu
 template <typename AT>
 int launch_zbb_path(const float* z_mean, const float* z_logvar, const float* eps_inj, long long numel, long long per_image,
@@ -36,9 +46,12 @@ int launch_finalize_stats_bb(const double* acc, int N, int n_ref, int H, int W, 
                              cudaStream_t st);
 int launch_distortion(const float* x, const float* xt, int N, int H, int W, int Ho, int Wo, float grad_scale, float* gx,
                       double* sse, double* sse_r, cudaStream_t st);
-int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st);
+int launch_finalize_stats(const double* acc, int N, int n_ref, int H, int W, float lmbda, float* out, cudaStream_t st,
+                          int* spi_advance = nullptr);
+double adam_lr_t(double lr, double beta1, double beta2, int iterations);
 int launch_adam(float* p, float* m, float* v, const float* ga, const float* gb, const float* fac, long long numel,
-                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st);
+                double lr, double beta1, double beta2, double eps, int iterations, float* g_out, cudaStream_t st,
+                const StepParams* spt = nullptr, const int* spi = nullptr);
 int launch_square(const float* x, long long n, float* o, cudaStream_t st);
 int launch_gdn_finish(const float* x, const float* nrm, long long n, int inverse, float* out, float* s_out,
                       cudaStream_t st);
@@ -97,8 +110,9 @@ int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __n
 int tc_conv_launch_igdn_bwd(const TcConv* c, const __nv_bfloat16* act_saved, const __nv_bfloat16* s_saved,
                             __nv_bfloat16* gx_out, cudaStream_t st);
 // w_ref (kh,kw,Cin,Cout) fp32 -> K-major bf16 B operand: [tap][Nn][K] (K = Cin for forward kinds, Cout for dgrads)
+// dup = 2 (forward kinds only): K = 2*Cin, the weights stacked twice along K for a hi|lo split input operand
 int launch_pack_weights_bf16(const float* w_ref, int taps, int Cin, int Cout, bool transposed, __nv_bfloat16* out,
-                             cudaStream_t st);
+                             cudaStream_t st, int dup = 1);
 int tc_selftest_available();
 
 }  // namespace sga

@@ -27,6 +27,22 @@ def shard_range(n, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def rank_segments(num_images, num_pixels_per_image, rank, world_size):
+    """Sharding ACROSS reference batches: the rank takes the contiguous global image range shard_range(num_images, ...) and
+    cuts it at the reference's batch boundaries.  Every segment lies inside one reference batch, so it runs as one engine
+    with that batch's n_ref (the 1/n_ref of every gradient, sga.py:147,150) and its own offset into the batch's noise
+    stream; all segments of a rank advance together.  A 100-image Tecnick input (15 batches of 7, 7, ..., 2) then keeps
+    12-13 images on each of 8 GPUs busy at once instead of 15 sequential passes with at most one image per GPU.
+    Returns [dict(batch, n_ref, lo, hi, first_in_batch)] with global [lo, hi)."""
+    lo, hi = shard_range(num_images, rank, world_size)
+    out = []
+    for b, (b_lo, b_hi) in enumerate(reference_batches(num_images, num_pixels_per_image)):
+        s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+        if s_lo < s_hi:
+            out.append(dict(batch=b, n_ref=b_hi - b_lo, lo=s_lo, hi=s_hi, first_in_batch=s_lo - b_lo))
+    return out
+
+
 def world():
     import os
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -78,3 +94,17 @@ def allreduce_scalars(vals, device="cuda"):
     t = torch.tensor(vals, dtype=torch.float64, device=device)
     dist.all_reduce(t)
     return [float(v) for v in t.cpu()]
+
+
+def allgather_floats(v, device="cuda"):
+    """One float per rank -> list over ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(v)]
+    if dist.get_backend() == "gloo":
+        device = "cpu"
+    t = torch.tensor([v], dtype=torch.float64, device=device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]

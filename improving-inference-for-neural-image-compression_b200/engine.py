@@ -121,6 +121,16 @@ class SgaEngine:
                                      _ptr(st["m_z"]), _ptr(st["v_z"]), float(temperature), int(step), _ptr(noise_y),
                                      _ptr(noise_z), _ptr(self.stats) if want_stats else None, _stream()))
 
+    def loop(self, x, st, temperatures, first_step, want_stats=True):
+        """len(temperatures) consecutive SGA iterations in place on the state dict, device-resident (graph replay on bf16
+        contexts): iteration k uses temperatures[k] and step first_step + k.  self.stats then holds the LAST iteration's
+        statistics."""
+        n = len(temperatures)
+        arr = (ctypes.c_float * max(n, 1))(*[float(t) for t in temperatures])
+        _lib.check(self.lib.sga_loop(self.ctx, _ptr(x), _ptr(st["y"]), _ptr(st["z"]), _ptr(st["m_y"]), _ptr(st["v_y"]),
+                                     _ptr(st["m_z"]), _ptr(st["v_z"]), arr, int(first_step), n,
+                                     _ptr(self.stats) if want_stats else None, _stream()))
+
     def eval_hard(self, x, y, z):
         """sga.py:240-247 -- hard-rounded latents. Returns dict of per-image numpy arrays."""
         _lib.check(self.lib.sga_eval_hard(self.ctx, _ptr(x), _ptr(y), _ptr(z), _ptr(self.stats), _stream()))
@@ -157,14 +167,17 @@ class SgaEngine:
         """x: float32 [n,H,W,3] in [0,1] on the device.  Returns (y, z, eval dict)."""
         y, z = self.encode_init(x)
         st = self.new_state(y, z)
-        for it in range(its):
-            T = annealed_temperature(it, r=annealing_rate, ub=T_ub, scheme="exp0", t0=t0)       # sga.py:211
-            at_log = log is not None and (it % log_itv == 0 or it + 1 == its)                    # sga.py:216
-            self.step(x, st, T, it, want_stats=at_log)
-            if at_log:
+        temps = [annealed_temperature(it, r=annealing_rate, ub=T_ub, scheme="exp0", t0=t0) for it in range(its)]  # sga.py:211
+        # iterations run in device-resident segments that end at the reference's log points (sga.py:216)
+        ends = [it for it in range(its) if it % log_itv == 0 or it + 1 == its] if log is not None else ([its - 1] if its else [])
+        first = 0
+        for end in ends:
+            self.loop(x, st, temps[first:end + 1], first, want_stats=log is not None)
+            if log is not None:
                 s = self.unpack_stats(self.stats.cpu().numpy())
                 extra = self.eval_hard(x, st["y"], st["z"]) if verbose else None
-                log(it, T, s, extra)
+                log(end, temps[end], s, extra)
+            first = end + 1
         return st["y"], st["z"], self.eval_hard(x, st["y"], st["z"])
 
 

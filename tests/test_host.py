@@ -271,3 +271,23 @@ def test_msssim_value_against_straight_line_numpy():
     assert abs(float(got[0]) - want) < 2e-6, (float(got[0]), want)
     same = msssim_per_image(torch.from_numpy(x[None].astype(np.float32)), torch.from_numpy(x[None].astype(np.float32)))
     assert abs(float(same[0]) - 1.0) < 1e-6
+
+
+def test_rank_segments_cover_every_image_once_and_stay_inside_one_reference_batch():
+    """Cross-batch sharding (Tecnick, BASELINE configs[3]): 100 images of 1200x1200 are 15 reference batches (7,...,7,2;
+    configs.py:5-9); every rank's contiguous global range is cut at the batch boundaries."""
+    from sga_b200.dist import rank_segments, reference_batches, shard_range
+    for n, px, ws in ((100, 1200 * 1200, 8), (100, 1200 * 1200, 3), (24, 768 * 512, 8), (5, 1200 * 1200, 8), (30, 768 * 512, 4)):
+        batches = reference_batches(n, px)
+        seen = np.zeros(n, dtype=int)
+        for r in range(ws):
+            segs = rank_segments(n, px, r, ws)
+            lo, hi = shard_range(n, r, ws)
+            assert sum(s["hi"] - s["lo"] for s in segs) == hi - lo
+            for s in segs:
+                b_lo, b_hi = batches[s["batch"]]
+                assert b_lo <= s["lo"] < s["hi"] <= b_hi and s["n_ref"] == b_hi - b_lo and s["first_in_batch"] == s["lo"] - b_lo
+                seen[s["lo"]:s["hi"]] += 1
+        assert (seen == 1).all()
+    per_gpu = [sum(s["hi"] - s["lo"] for s in rank_segments(100, 1200 * 1200, r, 8)) for r in range(8)]
+    assert max(per_gpu) == 13 and min(per_gpu) == 12          # every GPU busy with its whole share at once
