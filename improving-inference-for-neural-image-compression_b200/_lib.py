@@ -51,6 +51,8 @@ EXPORTS = [
     "sga_launch_count", "sga_profile_enable", "sga_profile_read", "sga_op_soft_round",
     "sga_op_eb_likelihood", "sga_op_gauss_likelihood", "sga_op_adam", "sga_op_conv", "sga_op_gdn", "sga_op_igdn_bwd",
     "sga_bb_hyper_init", "sga_bb_grad", "sga_bb_step", "sga_bb_eval",
+    "sga_eval_tilde", "sga_codec_create", "sga_codec_destroy", "sga_codec_create_host", "sga_codec_z_centers", "sga_codec_bin",
+    "sga_rc_encode", "sga_rc_decode",
 ]
 
 _lib = None
@@ -101,6 +103,14 @@ def load():
     lib.sga_bb_grad.argtypes = [vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.sga_bb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, i32, f64, vp, vp]
     lib.sga_bb_eval.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.sga_eval_tilde.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.sga_codec_create.argtypes = [vp, ctypes.POINTER(vp), vp]
+    lib.sga_codec_destroy.argtypes = [vp]
+    lib.sga_codec_create_host.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.sga_codec_z_centers.argtypes = [vp, vp, i32]
+    lib.sga_codec_bin.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.sga_rc_encode.argtypes = [vp, i32, i64, vp, vp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    lib.sga_rc_decode.argtypes = [vp, i32, i64, vp, vp, ctypes.c_uint64, vp]
     for name in EXPORTS:
         if name not in ("sga_last_error", "sga_workspace_bytes", "sga_launch_count"):
             getattr(lib, name).restype = ctypes.c_int

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsga_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "conv_plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_igdn_fwd_tc.cu", "igdn_tc.cu", "layer3_tc.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "conv_plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_igdn_fwd_tc.cu", "igdn_tc.cu", "layer3_tc.cu", "codec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

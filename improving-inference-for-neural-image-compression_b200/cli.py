@@ -232,6 +232,122 @@ def compress_bb(args, out=print):
     return results
 
 
+def parse_args_mbt2018(argv):
+    """tf_boilerplate.parse_args as mbt2018.py uses it: compress and decompress (training is out of scope)."""
+    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--verbose", "-V", action="store_true")
+    parser.add_argument("--num_filters", type=int, default=-1, help="Number of filters in the latents.")
+    parser.add_argument("--num_hfilters", type=int, default=-1)
+    parser.add_argument("--checkpoint_dir", default="./checkpoints", help="Directory where to save/load model checkpoints.")
+    sub = parser.add_subparsers(title="commands", dest="command")
+    c = sub.add_parser("compress", formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                       description="Reads an image / .npy batch, compresses it with the base model, writes RD statistics and, "
+                                   "with an output file, the bitstream.")
+    c.add_argument("--results_dir", default="./results")
+    c.add_argument("runname")
+    c.add_argument("input_file")
+    c.add_argument("output_file", nargs="?", help="bitstream file (the reference writes <input>.tfci when "
+                                                  "configs.write_tfci_for_eval is set)")
+    d = sub.add_parser("decompress", formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                       description="Reads a bitstream file, reconstructs the image(s), writes a PNG (one image) or .npy.")
+    d.add_argument("runname")
+    d.add_argument("input_file")
+    d.add_argument("output_file", nargs="?")
+    args = parser.parse_args(argv[1:])
+    if args.command is None:
+        parser.print_usage()
+        sys.exit(2)
+    return args
+
+
+def compress_mbt2018(args, out=print):
+    """The base model's one-shot compression (mbt2018.py:131-245): y = g_a(x), z = h_a(y), z_hat = round(z), y_hat =
+    round(y - mu) + mu, range-coded strings, the 7 eval fields plus batch_actual_bpp / batch_sizes /
+    avg_batch_actual_bpp, output rd-<runname>-file=<input>.npz."""
+    import torch
+    from . import codec as Cd
+    from . import dist as D
+    from . import weights as Wm
+    from .engine import EVAL_FIELDS, SgaEngine
+    from .msssim import msssim_per_image
+    X = load_input(args.input_file)
+    num_images, H, Wd = int(X.shape[0]), int(X.shape[1]), int(X.shape[2])
+    num_pixels = H * Wd
+    W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, args.num_filters)
+    results = {k: [] for k in EVAL_FIELDS}
+    batch_actual_bpp, batch_sizes, blobs = [], [], []
+    for (lo, hi) in D.reference_batches(num_images, num_pixels):
+        n = hi - lo
+        eng = SgaEngine(W, n, H, Wd, args.num_filters, 0.01, operand="f32")
+        cd = Cd.LatentCodec(eng)
+        x = torch.from_numpy(X[lo:hi].astype(np.float32) / 255.0).cuda()
+        y, z = eng.encode_init(x)
+        streams, y_hat, z_hat = cd.compress(y, z, Cd.MODE_MEAN_CENTRED)                    # mbt2018.py:84-85
+        ev = eng.eval_tilde(x, y_hat, z_hat)
+        ms = msssim_per_image(eng.reconstruction(), x)
+        rows = [ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"], ev["est_y_bpp"],
+                ev["est_z_bpp"]]
+        for k, v in zip(EVAL_FIELDS, rows):
+            results[k] += np.asarray(v).tolist()
+        packed = Cd.pack(streams, Cd.MODE_MEAN_CENTRED, args.num_filters, H, Wd)            # mbt2018.py:211-214
+        blobs.append(packed)
+        batch_actual_bpp.append(len(packed) * 8 / num_pixels)                              # mbt2018.py:220-221
+        batch_sizes.append(n)
+        cd.close()
+        eng.close()
+    if args.output_file:
+        with open(args.output_file, "wb") as f:                                            # mbt2018.py:215-217
+            f.write(blobs[0] if len(blobs) == 1 else b"".join(blobs))
+    results = {k: np.asarray(v) for k, v in results.items()}
+    results["batch_actual_bpp"] = np.asarray(batch_actual_bpp)
+    results["batch_sizes"] = np.asarray(batch_sizes)
+    results["avg_batch_actual_bpp"] = np.sum(batch_actual_bpp) / np.sum(batch_sizes)       # mbt2018.py:233
+    np.savez(os.path.join(args.results_dir, "rd-%s-file=%s.npz" % (args.runname, os.path.basename(args.input_file))), **results)
+    for k in EVAL_FIELDS + ["avg_batch_actual_bpp"]:
+        out("Avg {}: {:0.4f}".format(k, np.mean(results[k])))                             # mbt2018.py:243-245
+    return results
+
+
+def decompress_mbt2018(args, out=print):
+    """mbt2018.py:248-295: strings -> z_hat -> (mu, sigma) -> y_hat -> x_hat, written as PNG (one image) or .npy."""
+    import torch
+    from . import codec as Cd
+    from . import weights as Wm
+    from .engine import SgaEngine
+    with open(args.input_file, "rb") as f:
+        data = f.read()
+    streams, mode, C, H, Wd = Cd.unpack(data)
+    if args.num_filters > 0 and args.num_filters != C:
+        raise ValueError("bitstream was written with num_filters=%d, --num_filters says %d" % (C, args.num_filters))
+    W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, C)
+    eng = SgaEngine(W, len(streams), H, Wd, C, 0.01, operand="f32")
+    cd = Cd.LatentCodec(eng)
+    y_hat, z_hat = cd.decompress(streams, mode)
+    eng.eval_tilde(None, y_hat, z_hat)
+    xt = eng.reconstruction()
+    img = torch.round(torch.clamp(xt, 0, 1) * 255).to(torch.uint8).cpu().numpy()           # utils.write_png: saturate + round
+    dst = args.output_file or (args.input_file + (".png" if len(streams) == 1 else ".npy"))
+    if dst.endswith(".npy") or len(streams) != 1:
+        np.save(dst, img)
+    else:
+        from PIL import Image
+        Image.fromarray(img[0]).save(dst)
+    cd.close()
+    eng.close()
+    out("wrote %s" % dst)
+    return img
+
+
+def main_mbt2018(argv=None):
+    args = parse_args_mbt2018(sys.argv if argv is None else argv)
+    if args.command == "compress":
+        compress_mbt2018(args)
+    elif args.command == "decompress":
+        decompress_mbt2018(args)
+    else:
+        raise SystemExit("only compress / decompress are supported (training is out of scope)")
+
+
 def main(argv=None):
     args = parse_args(sys.argv if argv is None else argv)
     assert args.command == "compress", "Only compression is supported."     # sga.py:303

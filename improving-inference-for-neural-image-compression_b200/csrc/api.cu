@@ -272,6 +272,7 @@ static int forward_f32(sga_ctx* c, const float* x, const float* y, const float* 
   const float grad_scale =
       (g.lmbda > 0.0f) ? static_cast<float>(2.0 * 65025.0 * g.lmbda / (static_cast<double>(g.n_ref) * d.H * d.W * 3.0))
                        : 0.0f;
+  if (x == nullptr) return SGA_OK;          // decoder side: reconstruction only (sga_reconstruction reads f_xt)
   SGA_TRY(launch_distortion(x, c->f_xt, d.N, d.H, d.W, d.Hs[4], d.Ws[4], grad_scale, want_grad ? c->f_gx : nullptr,
                             c->acc + 2 * d.N, c->acc + 3 * d.N, st));
   if (stats) {
@@ -540,8 +541,10 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
   const bool bf = (cfg->operand == SGA_OPERAND_BF16);
   c->fused = bf && tc_conv_can_fuse(d.C) && getenv("SGA_NO_FUSE") == nullptr;
   {
+    // opt-in (SGA_SPLIT0=1): measured no accuracy gain even at |y| ~ 120 (test_grad_bf16_large_latents_and_the_split_operand)
+    // for +55 % time of g_s layer 0
     const char* es = getenv("SGA_SPLIT0");
-    c->split0 = (bf && cfg->variant == SGA_VARIANT_SGA && !(es != nullptr && es[0] == '0')) ? 1 : 0;
+    c->split0 = (bf && cfg->variant == SGA_VARIANT_SGA && es != nullptr && es[0] == '1') ? 1 : 0;
   }
   // ---- live across phases
   A(&c->acc, 5 * d.N);
@@ -901,6 +904,51 @@ int sga_eval_hard(sga_ctx* c, const float* x, const float* y, const float* z, fl
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
   SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are evaluated through sga_bb_eval");
   return forward_f32(c, x, y, z, 1.0f, 0, nullptr, nullptr, 1, false, stats, static_cast<cudaStream_t>(stream));
+}
+
+/* Everything downstream of given (y_tilde, z_tilde), fp32: the eval tensors of mbt2018.py:171-185 for the baseline's
+ * mean-centred quantisation, and -- with x = NULL -- the decoder's synthesis (mbt2018.py:275-283). */
+int sga_eval_tilde(sga_ctx* c, const float* x, const float* y_tilde, const float* z_tilde, float* stats, void* stream) {
+  SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
+  SGA_CHECK(c->cfg.variant == SGA_VARIANT_SGA, "bits-back contexts are evaluated through sga_bb_eval");
+  SGA_CHECK(y_tilde && z_tilde, "null latent");
+  return forward_f32(c, x, y_tilde, z_tilde, 1.0f, 0, nullptr, nullptr, 2, false, x ? stats : nullptr,
+                     static_cast<cudaStream_t>(stream));
+}
+
+/* ---- entropy coding (codec.cu) ------------------------------------------------------------------------------------ */
+int sga_codec_create(sga_ctx* c, sga_codec** out, void* stream) {
+  SGA_CHECK(c && c->bound && out, "bad argument (weights must be bound: the z tables come from the factorised prior)");
+  sga_codec* cd = codec_new();
+  const int rc = codec_build_tables(c->eb_pack, c->d.C, cd, static_cast<cudaStream_t>(stream));
+  if (rc != SGA_OK) { sga_codec_destroy(cd); return rc; }
+  *out = cd;
+  return SGA_OK;
+}
+
+/* Symbol binning.  z holds the hyper-latents (rounded here: z_hat = rint(z)); mu / sigma = h_s(z_hat) are evaluated with the
+ * fp32 kernels exactly as the decoder will evaluate them.  y (may be NULL on the decoder side) holds the latents;
+ * mode 0: y_hat = rint(y) (SGA result, sga.py:240-241), mode 1: y_hat = rint(y - mu) + mu (mbt2018.py baseline).
+ * Device outputs, one entry per latent element: tab_y / sym_y / base_y (y_hat = base_y + sym_y) / yhat (optional) and
+ * tab_z / sym_z (optional; z_hat = centre[channel] + sym_z). */
+int sga_codec_bin(sga_ctx* c, const sga_codec* cd, const float* y, const float* z, int32_t mode, int32_t* tab_y,
+                  int32_t* sym_y, float* base_y, float* yhat, int32_t* tab_z, int32_t* sym_z, void* stream) {
+  SGA_CHECK(c && c->bound && cd && z && tab_y && base_y, "bad argument");
+  SGA_CHECK(codec_num_channels(cd) == 0 || codec_num_channels(cd) == c->d.C, "codec was built for %d channels", codec_num_channels(cd));
+  SGA_CHECK(mode == 0 || mode == 1, "unknown quantisation mode %d", mode);
+  SGA_CHECK(y == nullptr || sym_y != nullptr, "sym_y is required when y is given");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dims& d = c->d;
+  const sga_config& g = c->cfg;
+  SGA_CUDA(cudaMemsetAsync(c->acc, 0, 5 * d.N * sizeof(double), st));
+  SGA_TRY(launch_z_path<float>(z, nullptr, d.nz, d.nz / d.N, d.C, c->eb_pack, 1.0f, g.clip_eps, g.seed, 0, 1, 0.0f, c->f_zt,
+                               nullptr, nullptr, c->acc + d.N, 0, st));
+  SGA_TRY(conv_f32(kUp2, c->hs[0], d.N, d.Hz, d.Wz, c->f_zt, true, 1, nullptr, c->f_h0, st));
+  SGA_TRY(conv_f32(kUp2, c->hs[1], d.N, 2 * d.Hz, 2 * d.Wz, c->f_h0, true, 1, nullptr, c->f_h1, st));
+  SGA_TRY(conv_f32(kS1True, c->hs[2], d.N, d.Hh, d.Wh, c->f_h1, true, 0, nullptr, c->h2, st));
+  SGA_TRY(launch_bin_y(y, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, mode, tab_y, sym_y, base_y, yhat, st));
+  if (tab_z && sym_z) SGA_TRY(launch_bin_z(z, d.nz, d.C, cd, tab_z, sym_z, st));
+  return SGA_OK;
 }
 
 int sga_reconstruction(sga_ctx* c, float* xt_out, void* stream) {

@@ -292,7 +292,7 @@ __global__ void k_z_path(const float* __restrict__ z, const float* __restrict__ 
       const long long e = e0 + k;
       if (e < numel) {
         float d = 0.0f, zt;
-        if (hard) zt = rintf(z[e]);
+        if (hard) zt = (hard == 2) ? z[e] : rintf(z[e]);      // 2: z already holds z_tilde
         else zt = soft_round_sel<FAST>(z[e], u[2 * k], u[2 * k + 1], T, eps, &d);
         EbParams P;
         eb_load(pk, C, static_cast<int>(e % C), P);
@@ -575,7 +575,7 @@ __global__ void k_y_path(const float* __restrict__ y, const float* __restrict__ 
       for (int k = 0; k < 2; ++k) {
         float d = 0.0f, yt;
         if (yt_in) yt = yk[k];
-        else if (hard) yt = rintf(yk[k]);
+        else if (hard) yt = (hard == 2) ? yk[k] : rintf(yk[k]);   // 2: y already holds y_tilde
         else yt = soft_round_sel<FAST>(yk[k], u[2 * k], u[2 * k + 1], T, eps, &d);
         float dpdy, dpdsb, sigma;
         const float p = FAST ? gauss_likelihood_fast(yt, muk[k], lsk[k], &dpdy, &dpdsb, &sigma)

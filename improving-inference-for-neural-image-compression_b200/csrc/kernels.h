@@ -61,6 +61,18 @@ int launch_igdn_bwd_finish(const float* g, const float* x, const float* s, const
 int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t st);
 
+// ---- codec.cu : quantised CDF tables, symbol binning, host range coder (reference mbt2018.py:84-85, 211-221, 248-295)
+}  // namespace sga
+struct sga_codec;
+namespace sga {
+int codec_build_tables(const float* eb_pack, int C, sga_codec* cd, cudaStream_t st);
+sga_codec* codec_new();
+// y may be nullptr (decoder side: only the table index and the base of every element are produced)
+int launch_bin_y(const float* y, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C, int mode, int* tab, int* sym,
+                 float* base, float* yhat, cudaStream_t st);
+int launch_bin_z(const float* z, long long numel, int C, const sga_codec* cd, int* tab, int* sym, cudaStream_t st);
+int codec_num_channels(const sga_codec* cd);
+
 // ---- conv_plan.cu : tap tables shared by the SIMT and tcgen05 paths
 struct ConvGeom {
   int kind, kh, kw;

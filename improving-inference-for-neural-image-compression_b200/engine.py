@@ -136,6 +136,12 @@ class SgaEngine:
         _lib.check(self.lib.sga_eval_hard(self.ctx, _ptr(x), _ptr(y), _ptr(z), _ptr(self.stats), _stream()))
         return self.unpack_stats(self.stats.cpu().numpy())
 
+    def eval_tilde(self, x, y_tilde, z_tilde):
+        """Everything downstream of given (y_tilde, z_tilde), fp32, nothing rounded (mbt2018.py:171-185 on the baseline's
+        mean-centred y_hat).  x = None: reconstruction only (the decoder's synthesis, mbt2018.py:275-283)."""
+        _lib.check(self.lib.sga_eval_tilde(self.ctx, _ptr(x), _ptr(y_tilde), _ptr(z_tilde), _ptr(self.stats), _stream()))
+        return None if x is None else self.unpack_stats(self.stats.cpu().numpy())
+
     def reconstruction(self):
         """x_tilde [n,H,W,3] (float, un-clipped) of the most recent fp32 forward (e.g. eval_hard)."""
         xt = torch.empty((self.n, self.h, self.w, 3), dtype=torch.float32, device=self.device)

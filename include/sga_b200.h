@@ -125,6 +125,37 @@ int sga_loop(sga_ctx* ctx, const float* x, float* y, float* z, float* m_y, float
  * y_tilde / z_tilde.  stats_out as above (rd_loss etc. computed on the rounded latents). */
 int sga_eval_hard(sga_ctx* ctx, const float* x, const float* y, const float* z, float* stats_out, void* stream);
 
+/* Everything downstream of GIVEN (y_tilde, z_tilde), always fp32, nothing rounded: the eval tensors of mbt2018.py:171-185
+ * for the baseline's mean-centred quantisation; with x = NULL only the reconstruction is produced (the decoder's synthesis,
+ * mbt2018.py:275-283; read it with sga_reconstruction). */
+int sga_eval_tilde(sga_ctx* ctx, const float* x, const float* y_tilde, const float* z_tilde, float* stats_out, void* stream);
+
+/* ---- entropy coding of the quantised latents (reference mbt2018.py:84-85 `string` / `side_string`, :211-221, :248-295;
+ * the reference calls tensorflow-compression's range-coding ops there).  A codec holds the quantised CDF tables: for y the
+ * Gaussian-conditional model on the 64 scales of sga.py:129 x 33 mean offsets, for z one table per channel from the
+ * factorised prior; both are built on the device.  Binning (table index + symbol per element) runs on the device, the
+ * range coder itself on the host. */
+typedef struct sga_codec sga_codec;
+int sga_codec_create(sga_ctx* ctx, sga_codec** out, void* stream);
+int sga_codec_destroy(sga_codec* codec);
+/* Host-only table set (coder tests, decoder-only use).  freq_*: per table len+1 frequencies (regular symbols, then the
+ * escape symbol), every table summing to 65536 with no zero entry; min_*: value of symbol index 0. */
+int sga_codec_create_host(int32_t n_tables_y, const int32_t* len_y, const int32_t* min_y, const uint32_t* freq_y,
+                          int32_t n_tables_z, const int32_t* len_z, const int32_t* min_z, const uint32_t* freq_z,
+                          sga_codec** out);
+int sga_codec_z_centers(const sga_codec* codec, int32_t* out, int32_t n_channels);
+/* z: hyper-latents, rounded inside (z_hat = rint(z)); y: latents or NULL (decoder).  mode 0: y_hat = rint(y) (sga.py:240),
+ * mode 1: y_hat = rint(y - mu) + mu (mbt2018.py baseline).  Device int32 / float arrays with one entry per latent element;
+ * y_hat = base_y + sym_y, z_hat = centre[channel] + sym_z.  yhat, tab_z, sym_z may be NULL. */
+int sga_codec_bin(sga_ctx* ctx, const sga_codec* codec, const float* y, const float* z, int32_t mode, int32_t* tab_y,
+                  int32_t* sym_y, float* base_y, float* yhat, int32_t* tab_z, int32_t* sym_z, void* stream);
+/* The range coder, HOST arrays.  which: 0 = y tables, 1 = z tables.  *nbytes receives the stream length (also when the
+ * capacity is too small, so the caller can retry). */
+int sga_rc_encode(const sga_codec* codec, int32_t which, int64_t n, const int32_t* tab, const int32_t* sym, uint8_t* out,
+                  uint64_t capacity, uint64_t* nbytes);
+int sga_rc_decode(const sga_codec* codec, int32_t which, int64_t n, const int32_t* tab, const uint8_t* bytes,
+                  uint64_t nbytes, int32_t* sym_out);
+
 /* Copies the cropped reconstruction x_tilde [n,H,W,3] (float, un-clipped) of the most recent fp32 forward
  * (sga_eval_hard, or sga_grad/sga_step with operand f32) -- used for MS-SSIM (sga.py:175) and PNG dumps. */
 int sga_reconstruction(sga_ctx* ctx, float* xt_out, void* stream);

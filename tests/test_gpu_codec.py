@@ -1,0 +1,103 @@
+"""Entropy coding on the device + host (csrc/codec.cu): decode(encode(y_hat, z_hat)) is bit-exact and the actual stream
+size agrees with the estimated rate (sga.py:143-147) -- the range-coder row of SURVEY.md 8f (mbt2018.py:84-85, 211-221,
+248-295)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_case
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _engine(W, n, h, w, C):
+    from sga_b200.engine import SgaEngine
+    return SgaEngine(W, n, h, w, C, 0.01, operand="f32")
+
+
+@pytest.mark.parametrize("C,n,h,w,mode", [(64, 2, 128, 192, 0), (64, 2, 128, 192, 1), (192, 1, 256, 256, 0), (32, 3, 75, 50, 0)])
+def test_latents_round_trip_bit_exact_and_size_matches_the_estimate(C, n, h, w, mode):
+    from sga_b200 import codec as Cd
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=C + mode)
+    eng = _engine(W, n, h, w, C)
+    cd = Cd.LatentCodec(eng)
+    yd, zd = (3.0 * y).cuda(), (2.0 * z).cuda()                   # spread the latents over more symbols
+    streams, y_hat, z_hat = cd.compress(yd, zd, mode)
+    if mode == 0:
+        assert torch.equal(y_hat, torch.round(yd))               # sga.py:240
+    assert torch.equal(z_hat, torch.round(zd))
+    y_dec, z_dec = cd.decompress(streams, mode)
+    assert torch.equal(z_dec, z_hat) and torch.equal(y_dec, y_hat)
+    # actual size vs the estimate the loop optimises (est_bpp of the same y_hat / z_hat), per image
+    ev = eng.eval_tilde(x.cuda(), y_hat, z_hat)
+    actual_y = np.array([len(s[1]) * 8.0 / (h * w) for s in streams])
+    actual_z = np.array([len(s[0]) * 8.0 / (h * w) for s in streams])
+    print("CODEC C=%d mode=%d est_y %s act_y %s est_z %s act_z %s" % (C, mode, ev["est_y_bpp"], actual_y, ev["est_z_bpp"], actual_z))
+    slack = 6 * 8.0 / (h * w)                                     # the coder's 5 flush bytes + rounding, per stream
+    assert np.all(np.abs(actual_y - ev["est_y_bpp"]) <= 0.01 * ev["est_y_bpp"] + slack), (actual_y, ev["est_y_bpp"])
+    assert np.all(np.abs(actual_z - ev["est_z_bpp"]) <= 0.01 * ev["est_z_bpp"] + slack), (actual_z, ev["est_z_bpp"])
+    # container
+    blob = Cd.pack(streams, mode, C, h, w)
+    s2, m2, C2, h2, w2 = Cd.unpack(blob)
+    assert s2 == streams and (m2, C2, h2, w2) == (mode, C, h, w)
+    cd.close()
+    eng.close()
+
+
+def test_escape_symbols_round_trip():
+    """Latents far outside every table's support (|y - mu| of thousands) take the escape path and still round-trip."""
+    from sga_b200 import codec as Cd
+    C, n, h, w = 32, 1, 64, 64
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=5)
+    y = y.clone()
+    y.view(-1)[::37] = 5000.0
+    y.view(-1)[5::41] = -70000.0
+    z = z.clone()
+    z.view(-1)[::13] = 900.0
+    eng = _engine(W, n, h, w, C)
+    cd = Cd.LatentCodec(eng)
+    streams, y_hat, z_hat = cd.compress(y.cuda(), z.cuda(), 0)
+    y_dec, z_dec = cd.decompress(streams, 0)
+    assert torch.equal(y_dec, y_hat) and torch.equal(z_dec, z_hat)
+    cd.close()
+    eng.close()
+
+
+def test_mbt2018_compress_decompress_cli(tmp_path):
+    """mbt2018.py compress -> bitstream + rd-*.npz (with batch_actual_bpp), decompress -> the same reconstruction."""
+    import sga_b200
+    from sga_b200.engine import SgaEngine
+    from sga_b200 import codec as Cd
+    C, h, w = 64, 96, 128
+    rn = sga_b200.weights.runname(C, 0.01)
+    Wd = sga_b200.weights.make_synthetic(C, 0)
+    sga_b200.weights.save_checkpoint(str(tmp_path / "ckpt"), rn, Wd)
+    from PIL import Image
+    img = sga_b200.synth.synthetic_images(1, h, w, 3)[0]
+    Image.fromarray(img).save(tmp_path / "in.png")
+    (tmp_path / "res").mkdir()
+    base = [sys.executable, os.path.join(ROOT, "mbt2018.py"), "--num_filters", str(C), "--checkpoint_dir", str(tmp_path / "ckpt")]
+    r = subprocess.run(base + ["compress", "--results_dir", str(tmp_path / "res"), rn, str(tmp_path / "in.png"),
+                               str(tmp_path / "out.tfci")], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Avg avg_batch_actual_bpp:" in r.stdout and "Avg est_bpp:" in r.stdout
+    d = np.load(tmp_path / "res" / ("rd-%s-file=in.png.npz" % rn))                             # mbt2018.py:241
+    for k in ("mse", "psnr", "msssim", "msssim_db", "est_bpp", "est_y_bpp", "est_z_bpp", "batch_actual_bpp", "batch_sizes",
+              "avg_batch_actual_bpp"):
+        assert k in d.files
+    size_bits = os.path.getsize(tmp_path / "out.tfci") * 8.0
+    assert abs(size_bits / (h * w) - float(d["batch_actual_bpp"][0])) < 1e-9
+    assert abs(float(d["avg_batch_actual_bpp"]) - float(d["est_bpp"][0])) <= 0.01 * float(d["est_bpp"][0]) + (22 + 16) * 8.0 / (h * w)
+    r = subprocess.run(base + ["decompress", rn, str(tmp_path / "out.tfci"), str(tmp_path / "rec.png")], capture_output=True,
+                       text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    rec = np.asarray(Image.open(tmp_path / "rec.png"))
+    # the same reconstruction as the encoder side evaluates: PSNR of the decoded PNG == the npz's psnr
+    mse = np.mean((rec.astype(np.float64) - img.astype(np.float64)) ** 2)
+    psnr = 20 * np.log10(255.0) - 10 * np.log10(mse)
+    assert abs(psnr - float(d["psnr"][0])) < 1e-3, (psnr, float(d["psnr"][0]))

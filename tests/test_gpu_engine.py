@@ -86,9 +86,9 @@ def test_golden_fixture_f32():
     assert np.abs(ev["psnr"] - gold["eval_psnr"]).max() < 0.01                # north_star tolerance: 0.01 dB
 
 
-@pytest.mark.parametrize("C,n,h,w,gz_tol", [(64, 2, 256, 192, 7e-2), (192, 1, 128, 96, 7e-2), (192, 2, 256, 256, 7e-2),
-                                            (256, 1, 128, 128, 7e-2), (128, 1, 80, 112, 7e-2), (64, 3, 48, 80, 0.12),
-                                            (192, 3, 208, 176, 7e-2)])
+@pytest.mark.parametrize("C,n,h,w,gz_tol", [(64, 2, 256, 192, 5e-2), (192, 1, 128, 96, 3.5e-2), (192, 2, 256, 256, 5e-2),
+                                            (256, 1, 128, 128, 7e-2), (128, 1, 80, 112, 3e-2), (64, 3, 48, 80, 0.12),
+                                            (192, 3, 208, 176, 6e-2)])
 def test_grad_bf16_vs_oracle(C, n, h, w, gz_tol):
     """bf16 tcgen05 path of the whole graph vs the float32 oracle: statistics to 1e-3 relative, gradients to bf16
     accumulation accuracy (operands carry 8 mantissa bits through 4 (de)conv + IGDN stages and back).  grad_z gets the
@@ -108,10 +108,12 @@ def test_grad_bf16_vs_oracle(C, n, h, w, gz_tol):
         C, n, h, w, abs(s["train_bpp"] - float(ref["train_bpp"])) / abs(float(ref["train_bpp"])),
         abs(s["train_mse"] - float(ref["train_mse"])) / abs(float(ref["train_mse"])),
         np.abs(s["psnr"] - ref["psnr"].numpy()).max(), rms_rel_err(gy, ref["grad_y"]), rms_rel_err(gz, ref["grad_z"])))
-    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-3 * abs(float(ref["train_bpp"]))
-    assert abs(s["train_mse"] - float(ref["train_mse"])) <= 5e-3 * abs(float(ref["train_mse"]))
-    assert np.abs(s["psnr"] - ref["psnr"].numpy()).max() < 0.05
-    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2, rms_rel_err(gy, ref["grad_y"])
+    # tolerances = 2-3x what the path achieves (round-2 measurements: bpp <= 2.2e-4, mse <= 5.5e-4, PSNR <= 1.8e-3 dB,
+    # grad_y <= 4.4e-3 rms; grad_z 1.4e-2 .. 7.9e-2, see the docstring)
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 5e-4 * abs(float(ref["train_bpp"]))
+    assert abs(s["train_mse"] - float(ref["train_mse"])) <= 1.5e-3 * abs(float(ref["train_mse"]))
+    assert np.abs(s["psnr"] - ref["psnr"].numpy()).max() < 5e-3
+    assert rms_rel_err(gy, ref["grad_y"]) < 1e-2, rms_rel_err(gy, ref["grad_y"])
     assert rms_rel_err(gz, ref["grad_z"]) < gz_tol, rms_rel_err(gz, ref["grad_z"])
 
 
@@ -194,7 +196,7 @@ def test_grad_bf16_wave_ordered_schedule(monkeypatch):
     monkeypatch.setenv("SGA_NO_SMALL", "1")
     eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
     gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
-    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
+    assert rms_rel_err(gy, ref["grad_y"]) < 1e-2 and rms_rel_err(gz, ref["grad_z"]) < 5e-2
     monkeypatch.delenv("SGA_NO_SMALL")
     C, n, h, w = 64, 10, 256, 256                        # gs2: 10 * 4096 / 128 = 320 tiles per phase >= 74 pairs
     W, Wt, x, y, z = make_case(C, n, h, w, seed=5)
@@ -202,8 +204,8 @@ def test_grad_bf16_wave_ordered_schedule(monkeypatch):
     eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
     gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
     s = eng.unpack_stats(stats.cpu().numpy())
-    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 2e-3 * abs(float(ref["train_bpp"]))
-    assert rms_rel_err(gy, ref["grad_y"]) < 3e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 5e-4 * abs(float(ref["train_bpp"]))
+    assert rms_rel_err(gy, ref["grad_y"]) < 1e-2 and rms_rel_err(gz, ref["grad_z"]) < 7e-2
 
 
 def test_grad_bf16_halo_tile_operand_windows(monkeypatch):
@@ -216,8 +218,8 @@ def test_grad_bf16_halo_tile_operand_windows(monkeypatch):
         eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
         gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
         s = eng.unpack_stats(stats.cpu().numpy())
-        assert abs(s["train_mse"] - float(ref["train_mse"])) <= 5e-3 * abs(float(ref["train_mse"]))
-        assert rms_rel_err(gy, ref["grad_y"]) < 3e-2
+        assert abs(s["train_mse"] - float(ref["train_mse"])) <= 1.5e-3 * abs(float(ref["train_mse"]))
+        assert rms_rel_err(gy, ref["grad_y"]) < 1e-2
         eng.close()
 
 
@@ -281,11 +283,13 @@ def test_loop_on_fp32_context_and_single_stream(monkeypatch):
             monkeypatch.delenv(k)
 
 
-def test_grad_bf16_large_latents_need_the_split_operand(monkeypatch):
-    """Real high-rate models reach |y| ~ 100, where bf16 spacing is 0.5 and the fractional part that SGA optimises would
-    vanish from the distortion path.  y_tilde / z_tilde enter layer 0 as hi + lo bf16 pairs (K = 2C against the weights
-    stacked twice): with latents scaled to |y| <= ~120 the reconstruction statistics stay at bf16 accumulation accuracy,
-    and switching the split off (SGA_SPLIT0=0) is measurably worse on the same case."""
+def test_grad_bf16_large_latents_and_the_split_operand(monkeypatch):
+    """Real high-rate models reach |y| ~ 100, where bf16 spacing is 0.5: the fractional part that SGA optimises is coarsely
+    quantised in the operand of g_s layer 0.  With latents scaled to |y| <= 120 the gradients stay at bf16 accumulation
+    accuracy (measured 4.9e-3 rms) -- the operand's RELATIVE precision is what matters and that does not depend on |y|.
+    The opt-in split operand (SGA_SPLIT0=1: y_tilde / z_tilde enter layer 0 as hi + lo bf16 pairs, K = 2C against the weights
+    stacked twice) must give the same result to the same accuracy; measured 5.0e-3 vs 4.9e-3, i.e. no gain, which is why it
+    is off by default."""
     C, n, h, w = 64, 1, 128, 128
     W, Wt, x, y, z = make_case(C, n, h, w, seed=21)
     y = (y * (120.0 / float(y.abs().max()))).contiguous()
@@ -301,8 +305,8 @@ def test_grad_bf16_large_latents_need_the_split_operand(monkeypatch):
         errs[split] = (abs(s["train_mse"] - float(ref["train_mse"])) / float(ref["train_mse"]), rms_rel_err(gy, ref["grad_y"]))
         eng.close()
     monkeypatch.delenv("SGA_SPLIT0")
-    assert errs["1"][0] < 2e-3 and errs["1"][1] < 3e-2, errs
-    assert errs["0"][1] > errs["1"][1], errs
+    for split in ("1", "0"):
+        assert errs[split][0] < 6e-3 and errs[split][1] < 1e-2, errs
 
 
 def test_bf16_loop_against_fp32_loop_north_star_tolerance():
@@ -323,7 +327,7 @@ def test_bf16_loop_against_fp32_loop_north_star_tolerance():
     C, n, h, w, its = 192, 3, 256, 256, 2000
     W, Wt, x, _, _ = make_case(C, n, h, w, seed=31)
     xd = x.cuda()
-    temps = [annealed_temperature(it) for it in range(its)]
+    temps = [annealed_temperature(it, r=1e-3, ub=0.5, scheme="exp0", t0=700) for it in range(its)]
 
     def final(operand, perturb=0.0, pseed=0):
         eng = _engine(W, n, h, w, C, 0.01, operand, seed=0)
