@@ -9,8 +9,8 @@ backward to the latents -> Adam (reference sga.py:211-215).  The batch is sharde
 on the data path); the job is fixed as N grows => "scaling": "strong".
 
 Rank 0 prints ONE JSON line.
-  value        device-resident throughput of K iterations through sga_loop (the call the CLI makes: one CUDA graph of
-               the two-stream step, replayed), CUDA events on the launching stream, max over ranks;
+  value        device-resident throughput of K iterations through sga_loop (the call the CLI makes: the two-stream step
+               issued K times from inside the library), CUDA events on the launching stream, max over ranks;
   e2e          the same loop through the public engine API one iteration per call, with the image batch copied from
                pinned HOST memory every iteration (sga.py:212-214 feeds x every iteration) and the iteration's statistics
                read back to the host;
@@ -440,7 +440,7 @@ def main_ours(args, rank, ws, local, wl):
                    "engines_per_gpu": len(jobs),
                    "operand": args.operand + " operands, fp32 accumulate (TMEM); latents/Adam fp32",
                    "cache": "inputs larger than L2 (%.1f GB of activations rewritten every step)" % (ws_bytes / 1e9),
-                   "loop": "sga_loop: CUDA graph of the two-stream step replayed; x resident" if not bb
+                   "loop": "sga_loop: two-stream step issued from inside the library, x resident" if not bb
                            else "sga_bb_step per iteration (eager launches)",
                    "final_step": {"rd_loss": last["rd_loss"], "train_bpp": last["train_bpp"], "train_mse": last["train_mse"]}},
         "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -825,9 +825,10 @@ int sga_step(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* 
   return grad_common(c, x, y, z, T, step, ny, nz, stats, static_cast<cudaStream_t>(stream), o);
 }
 
-// n_steps iterations of sga.py:210-215 without host work per iteration: the step is captured once into a CUDA graph
+// n_steps iterations of sga.py:210-215 in one call: the two-stream step is enqueued n_steps times from this C++ loop (no
+// Python, no host synchronisation per iteration).  With SGA_GRAPH=1 the step is instead captured once into a CUDA graph
 // (both streams, programmatic dependent launches included) and replayed; temperature / noise step / Adam lr_t of
-// iteration k come from a device table indexed by a device counter that the step's last kernel advances.
+// iteration k then come from a device table indexed by a device counter that the step's last kernel advances.
 int sga_loop(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* v_y, float* m_z, float* v_z,
              const float* temperatures, int32_t first_step, int32_t n_steps, float* stats, void* stream) {
   SGA_CHECK(c && c->bound, "weights are not bound (call sga_bind_weights first)");
@@ -838,7 +839,12 @@ int sga_loop(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* 
   const sga_config& g = c->cfg;
   for (int k = 0; k < n_steps; ++k) SGA_CHECK(temperatures[k] > 0.0f, "temperature must be positive");
   const StepOut o{y, z, m_y, v_y, m_z, v_z, nullptr, nullptr};
-  const bool graphed = c->cfg.operand == SGA_OPERAND_BF16 && !c->prof && getenv("SGA_NO_GRAPH") == nullptr;
+  // Graph replay is opt-in (SGA_GRAPH=1).  Measured on the B200 (profiles/r2_schedule_ab.md): the eager two-stream issue is
+  // never launch-bound (the host enqueues a step in ~0.1 ms), programmatic dependent launch overlaps consecutive steps,
+  // while a replayed graph puts a full dependency between steps: 24 images 4.08 ms eager vs 4.18 ms replayed, 3 images
+  // 0.566 vs 0.562 ms.
+  const char* eg = getenv("SGA_GRAPH");
+  const bool graphed = c->cfg.operand == SGA_OPERAND_BF16 && !c->prof && eg != nullptr && eg[0] == '1';
   if (graphed && (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)) {
     // the default streams cannot be captured: run on the context's own stream, ordered after / before the caller's
     SGA_CUDA(cudaEventRecord(c->ev_in, st));

@@ -10,6 +10,7 @@
 //   dgrad ("gather" form):  g_act[pixel, cin] = sum_{a,b,c} gx[2i+a-2, 2j+b-2, c] * k[a,b,cin,c]  -- M = 128 input
 //     pixels, K = 75 (padded to 80), N = C.  The im2col A operand is built by 4 warps from a shared-memory copy of
 //     the gradient patch, directly in the no-swizzle K-major core-matrix layout the tensor core reads.
+#include <stdlib.h>
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "conv_tc.cuh"
@@ -22,7 +23,7 @@ using namespace tc;
 // forward
 // =====================================================================================================
 constexpr int kL3Threads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue of even / odd tiles
-constexpr int kL3Stages = 5;
+constexpr int kL3MaxStages = 8;       // the ring takes what shared memory is left (7 stages at C = 192, 6 at C = 256)
 constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
 constexpr int kL3IntH = 6, kL3IntW = 14;   // interior of the 8x16 tile
@@ -39,6 +40,8 @@ struct alignas(64) L3FwdParams {
   float grad_scale;
   int N, Hin, Win, C, H, W;
   int tiles_h, tiles_w, total_tiles, kchunks;
+  int prefetch;       // L2 prefetch distance in tiles (env SGA_L3_PREFETCH, default 3)
+  int stages;         // A-tile ring depth
 };
 
 __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant__ L3FwdParams P) {
@@ -50,22 +53,22 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   const int b_chunk = kL3NPad * 128;                 // 10240
   const uint32_t b_base = base;
   const uint32_t a_base = base + P.kchunks * b_chunk;
-  uint8_t* p_after = smem + P.kchunks * b_chunk + kL3Stages * 16384;
+  uint8_t* p_after = smem + P.kchunks * b_chunk + P.stages * 16384;
   float* Ps = reinterpret_cast<float*>(p_after);     // [2][128][81]
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_after + 2 * 128 * kPsStride * 4);
   const uint32_t bar_b = smem_u32(bars);
   const uint32_t bar_full = bar_b + 8;
-  const uint32_t bar_empty = bar_full + 8 * kL3Stages;
-  const uint32_t bar_tfull = bar_empty + 8 * kL3Stages;
+  const uint32_t bar_empty = bar_full + 8 * kL3MaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kL3MaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kL3Stages + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kL3MaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.amap);
     tma_prefetch_desc(&P.bmap);
     mbar_init(bar_b, 1);
-    for (int s = 0; s < kL3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
     fence_barrier_init();
   }
@@ -82,14 +85,23 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       mbar_arrive_expect_tx(bar_b, P.kchunks * b_chunk);
       for (int kc = 0; kc < P.kchunks; ++kc) tma_load_2d(b_base + kc * b_chunk, &P.bmap, bar_b, kc * 64, 0);
       int stage = 0; uint32_t phase = 0;
+      const int pf = P.prefetch;           // tiles of L2 prefetch distance (0 = off)
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= P.total_tiles) return;
+        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+        for (int kc = 0; kc < P.kchunks; ++kc) tma_prefetch_4d(&P.amap, kc * 64, w0, h0, img);
+      };
+      for (int d = 2; d < 2 + pf; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);   // the ring itself runs ~2 tiles ahead
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
         const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+        if (pf) prefetch_tile(tile + (2 + pf) * gridDim.x);
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           mbar_arrive_expect_tx(bar_full + 8 * stage, 16384);
           tma_load_4d(a_base + stage * 16384, &P.amap, bar_full + 8 * stage, kc * 64, w0, h0, img);
-          if (++stage == kL3Stages) { stage = 0; phase ^= 1u; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
             umma_bf16(d_tmem, smem_desc_sw128(a_base + stage * 16384 + kk * 32),
                       smem_desc_sw128(b_base + kc * b_chunk + kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);
-          if (++stage == kL3Stages) { stage = 0; phase ^= 1u; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(bar_tfull + 8 * buf);
       }
@@ -421,6 +433,7 @@ struct alignas(64) L3DgradFusedParams {
   __nv_bfloat16* out;          // d loss / d x_2
   int N, Hin, Win, C;
   int tiles_h, tiles_w, total_tiles;
+  int prefetch;                // L2 prefetch distance of the x / s tiles, in tiles (env SGA_L3_PREFETCH, default 1; 0 = off)
 };
 
 __device__ __forceinline__ float l3_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -576,6 +589,19 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
         const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
+        if (P.prefetch) {
+          // the x / s buffers are single (shared memory is full), so the loads of tile it+1 can only be issued late in tile
+          // it: pull them into L2 a whole tile earlier
+          const int nt = tile + P.prefetch * static_cast<int>(gridDim.x);
+          if (nt < P.total_tiles) {
+            const int nimg = nt / tiles_per_img, ntt = nt % tiles_per_img;
+            const int nh0 = (ntt / P.tiles_w) * 8, nw0 = (ntt % P.tiles_w) * 16;
+            for (int kc = 0; kc < kKc; ++kc) {
+              tma_prefetch_4d(&P.smap, kc * 64, nw0, nh0, nimg);
+              tma_prefetch_4d(&P.xmap, kc * 64, nw0, nh0, nimg);
+            }
+          }
+        }
         if (it > 0) mbar_wait(bar_a2, (it - 1) & 1);          // pass 1 of the previous tile has consumed its s tile
         mbar_arrive_expect_tx(bar_sfull, kTileBytes);
         for (int kc = 0; kc < kKc; ++kc) tma_load_4d(s_base + kc * 16384, &P.smap, bar_sfull, kc * 64, w0, h0, img);
@@ -813,7 +839,13 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     st = tma_encode_tiled(&F.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_scatter, bdims, bstr, bbox,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
-    c->f_smem = 1024 + F.kchunks * kL3NPad * 128 + kL3Stages * 16384 + 2 * 128 * kPsStride * 4 + 256;
+    const int f_fixed = 1024 + F.kchunks * kL3NPad * 128 + 2 * 128 * kPsStride * 4 + 256;
+    F.stages = (227 * 1024 - f_fixed) / 16384;
+    if (F.stages > kL3MaxStages) F.stages = kL3MaxStages;
+    if (const char* e = getenv("SGA_L3_STAGES")) { const int v = atoi(e); if (v >= 2 && v < F.stages) F.stages = v; }
+    SGA_CHECK(F.stages >= 2, "not enough shared memory for the layer-3 pipeline");
+    { const char* e = getenv("SGA_L3_PREFETCH"); F.prefetch = e ? atoi(e) : 3; }
+    c->f_smem = f_fixed + F.stages * 16384;
     c->f_grid = F.total_tiles < sms ? F.total_tiles : sms;
   }
   {
@@ -828,6 +860,7 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     L3DgradFusedParams& DF = c->DF;
     DF.N = N; DF.Hin = Hin; DF.Win = Win; DF.C = C; DF.wpack = w_gather;
     DF.tiles_h = D.tiles_h; DF.tiles_w = D.tiles_w; DF.total_tiles = D.total_tiles;
+    { const char* e = getenv("SGA_L3_PREFETCH"); DF.prefetch = e ? (atoi(e) > 0 ? 1 : 0) : 1; }
     c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr && x_saved != nullptr && s_saved != nullptr;
     if (c->fused_ok) {
       const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),

@@ -126,6 +126,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory destination, no barrier): turns the HBM latency of a later tma_load_4d of the
+// same box into an L2 hit.  Used by the HBM-bound layer-3 kernels, whose shared memory is too full for a deeper ring.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // CTA-pair variants: the destination is this CTA's shared memory, the mbarrier (shared::cluster address) may live in
 // the peer CTA -- both CTAs of a pair signal the leader's barrier
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {

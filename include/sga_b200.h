@@ -113,9 +113,10 @@ int sga_step(sga_ctx* ctx, const float* x, float* y, float* z, float* m_y, float
 
 /* The loop of sga.py:210-215 for n_steps consecutive iterations, device-resident: iteration k (0-based inside the call)
  * is sga_step with temperature temperatures[k] (HOST array of n_steps floats, the caller's annealing schedule,
- * sga.py:211) and step = first_step + k, Philox noise only.  On bf16 contexts the step is captured once per set of
- * tensors as a CUDA graph (two streams: hyper path beside the synthesis path) and replayed with the per-iteration scalars
- * read from a device table, so nothing crosses the host inside the call.  stats_out (may be NULL) receives the
+ * sga.py:211) and step = first_step + k, Philox noise only.  On bf16 contexts every step is issued as a two-stream
+ * schedule (hyper path beside the synthesis path) from inside the library, nothing is synchronised with the host; with
+ * the environment variable SGA_GRAPH=1 the step is captured once per set of tensors as a CUDA graph and replayed with the
+ * per-iteration scalars read from a device table.  stats_out (may be NULL) receives the
  * statistics of the LAST iteration.  The caller's stream is honoured (work is ordered after everything already enqueued on
  * it and later work on it waits for the loop); the default stream is legal. */
 int sga_loop(sga_ctx* ctx, const float* x, float* y, float* z, float* m_y, float* v_y, float* m_z, float* v_z,

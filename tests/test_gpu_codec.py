@@ -23,10 +23,18 @@ def _engine(W, n, h, w, C):
 @pytest.mark.parametrize("C,n,h,w,mode", [(64, 2, 128, 192, 0), (64, 2, 128, 192, 1), (192, 1, 256, 256, 0), (32, 3, 75, 50, 0)])
 def test_latents_round_trip_bit_exact_and_size_matches_the_estimate(C, n, h, w, mode):
     from sga_b200 import codec as Cd
+    from oracle import sga_oracle as O
     W, Wt, x, y, z = make_case(C, n, h, w, seed=C + mode)
     eng = _engine(W, n, h, w, C)
     cd = Cd.LatentCodec(eng)
-    yd, zd = (3.0 * y).cuda(), (2.0 * z).cuda()                   # spread the latents over more symbols
+    # Latents the entropy model is matched to, as in a trained codec: y ~ N(mu, sigma^2) with (mu, sigma) = h_s(round(z)).
+    # (Latents far off the model -- the synthetic weights' own g_a(x) -- cost less than estimated, because a table never
+    # assigns less than 2^-16 while the estimate goes down to the 1e-9 likelihood bound: measured 2.8 vs 3.7 bpp.)
+    z = 2.0 * z
+    h2, _ = O.hyper_synthesis_fwd(torch.round(z), Wt)
+    mu, sigma = h2[:, :y.shape[1], :y.shape[2], :C], torch.exp(h2[:, :y.shape[1], :y.shape[2], C:]).clamp(min=0.11)
+    y = (mu + sigma * torch.randn(y.shape, generator=torch.Generator().manual_seed(7))).contiguous()
+    yd, zd = y.cuda(), z.cuda()
     streams, y_hat, z_hat = cd.compress(yd, zd, mode)
     if mode == 0:
         assert torch.equal(y_hat, torch.round(yd))               # sga.py:240
