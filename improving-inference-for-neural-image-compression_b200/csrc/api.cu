@@ -952,7 +952,7 @@ int sga_codec_bin(sga_ctx* c, const sga_codec* cd, const float* y, const float* 
   SGA_TRY(conv_f32(kUp2, c->hs[0], d.N, d.Hz, d.Wz, c->f_zt, true, 1, nullptr, c->f_h0, st));
   SGA_TRY(conv_f32(kUp2, c->hs[1], d.N, 2 * d.Hz, 2 * d.Wz, c->f_h0, true, 1, nullptr, c->f_h1, st));
   SGA_TRY(conv_f32(kS1True, c->hs[2], d.N, d.Hh, d.Wh, c->f_h1, true, 0, nullptr, c->h2, st));
-  SGA_TRY(launch_bin_y(y, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, mode, tab_y, sym_y, base_y, yhat, st));
+  SGA_TRY(launch_bin_y(cd, y, c->h2, d.N, d.Hy, d.Wy, d.Hh, d.Wh, d.C, mode, tab_y, sym_y, base_y, yhat, st));
   if (tab_z && sym_z) SGA_TRY(launch_bin_z(z, d.nz, d.C, cd, tab_z, sym_z, st));
   return SGA_OK;
 }

@@ -4,8 +4,9 @@
 // kernels of a third-party package, not in /root/reference); sga.py itself only ESTIMATES the rate.  What is built here:
 //
 //   device  k_gauss_tables : quantised CDFs (16-bit precision) of  N(delta, s_i^2) * U(-1/2, 1/2)  on the integers for the 64
-//                            scales s_i = exp(linspace(log .11, log 256, 64)) (sga.py:129 / mbt2018.py:74) x 33 mean offsets
-//                            delta = j/32 - 1/2: the Gaussian-conditional model evaluated where the estimate evaluates it
+//                            scales s_i = exp(linspace(log .11, log 256, 64)) (sga.py:129 / mbt2018.py:74) x a grid of mean
+//                            offsets delta in [-1/2, 1/2] (step 1/128 for small scales .. 1/8 for large ones): the
+//                            Gaussian-conditional model evaluated where the estimate evaluates it
 //           k_eb_tables    : the same for the factorised prior of z, one table per channel (sga.py:100-104)
 //           k_bin_y/k_bin_z: per element, the table it is coded with and its symbol (the "binning")
 //   host    a 32-bit range coder (carry-propagating byte-wise renormalisation, 16-bit frequencies) with an escape symbol per
@@ -25,7 +26,10 @@ namespace sga {
 constexpr int kCdfBits = 16;
 constexpr uint32_t kCdfTotal = 1u << kCdfBits;
 constexpr int kScaleLevels = 64;        // SCALES_LEVELS (sga.py:26)
-constexpr int kMeanOffsets = 33;        // delta in {-16..16}/32
+// Mean offsets delta = mu - rint(mu) are quantised on a grid whose step shrinks with the scale: what matters is delta /
+// sigma (a 1/64 error at sigma = 0.11 moves a 50/50 split by 6 %, about 1 % in bits; measured +1.4 % total at 1/32).
+__host__ __device__ inline int codec_offset_res(int i) { return i < 23 ? 128 : (i < 40 ? 32 : 8); }   // sigma < 1.9 / < 15.5
+constexpr int kMaxTables = 64 * 129;
 constexpr double kScaleMin = 0.11, kScaleMax = 256.0;   // SCALES_MIN / SCALES_MAX (sga.py:24-25)
 constexpr int kEbRadius = 96;           // support of a factorised-prior table: median +- 96, escape beyond
 
@@ -61,13 +65,16 @@ __device__ void integerise_table(const double* __restrict__ pmf, int L, uint32_t
 
 __device__ __forceinline__ double std_cdf_d(double x) { return 0.5 * erfc(-0.70710678118654752440 * x); }
 
-// table t = scale i * kMeanOffsets + offset j; symbols k = -R..R map to indices 0..2R
-__global__ void k_gauss_tables(const int* __restrict__ tab_off, uint32_t* __restrict__ cdf, double* __restrict__ scratch,
-                               int scratch_stride) {
+// table t = tab_base[scale i] + offset index j (j = 0 .. res_i, delta = j / res_i - 1/2); symbols k = -R..R map to
+// indices 0..2R
+__global__ void k_gauss_tables(const int* __restrict__ tab_base, const int* __restrict__ tab_off, uint32_t* __restrict__ cdf,
+                               double* __restrict__ scratch, int scratch_stride) {
   const int t = blockIdx.x;
-  const int i = t / kMeanOffsets, j = t % kMeanOffsets;
+  int i = 0;
+  while (i + 1 < kScaleLevels && tab_base[i + 1] <= t) ++i;
+  const int j = t - tab_base[i];
   const double s = codec_scale(i);
-  const double delta = (j - (kMeanOffsets - 1) / 2) / 32.0;
+  const double delta = static_cast<double>(j) / codec_offset_res(i) - 0.5;
   const int R = codec_radius(s), L = 2 * R + 1;
   double* pmf = scratch + static_cast<size_t>(t) * scratch_stride;
   for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -134,8 +141,8 @@ __global__ void k_eb_tables(const float* __restrict__ pk, int C, int* __restrict
 // base = rint(mu) under the table with offset delta = mu - base; mode 1 (mbt2018.py baseline, tfc's mean-centred
 // quantisation): symbol = rint(y - mu), table offset 0, y_hat = symbol + mu.
 __global__ void k_bin_y(const float* __restrict__ y, const float* __restrict__ h2, int N, int Hy, int Wy, int Hh, int Wh,
-                        int C, int mode, int* __restrict__ tab, int* __restrict__ sym, float* __restrict__ base_out,
-                        float* __restrict__ yhat_out) {
+                        int C, int mode, const int* __restrict__ tab_base, int* __restrict__ tab, int* __restrict__ sym,
+                        float* __restrict__ base_out, float* __restrict__ yhat_out) {
   const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long numel = static_cast<long long>(N) * Hy * Wy * C;
   if (e >= numel) return;
@@ -155,7 +162,7 @@ __global__ void k_bin_y(const float* __restrict__ y, const float* __restrict__ h
   float base;
   if (mode == 0) {
     base = rintf(mu);
-    oj = static_cast<int>(rintf((mu - base) * 32.0f));          // in [-16, 16]
+    oj = static_cast<int>(rintf((mu - base) * static_cast<float>(codec_offset_res(si))));   // in [-res/2, res/2]
     if (y) {
       k = static_cast<int>(rintf(y[e]) - base);
       if (yhat_out) yhat_out[e] = rintf(y[e]);
@@ -168,7 +175,7 @@ __global__ void k_bin_y(const float* __restrict__ y, const float* __restrict__ h
       if (yhat_out) yhat_out[e] = static_cast<float>(k) + mu;
     }
   }
-  tab[e] = si * kMeanOffsets + oj + (kMeanOffsets - 1) / 2;
+  tab[e] = tab_base[si] + oj + codec_offset_res(si) / 2;
   if (y) sym[e] = k;
   base_out[e] = base;
 }
@@ -200,6 +207,7 @@ struct sga_codec {
   TableSet y, z;
   int C = 0;
   int* d_center = nullptr;     // device: centre of every channel's z table
+  int* d_tab_base = nullptr;   // device: first y table of every scale
 };
 
 namespace sga {
@@ -317,23 +325,29 @@ static int rc_decode(const TableSet& T, long long n, const int* tab, const uint8
 // pk: packed factorised-prior parameters of the context (elementwise.cu k_eb_pack)
 int codec_build_tables(const float* eb_pack, int C, sga_codec* cd, cudaStream_t st) {
   // ---- Gaussian tables
-  const int nt = kScaleLevels * kMeanOffsets;
+  int tab_base[kScaleLevels + 1];
+  tab_base[0] = 0;
+  for (int i = 0; i < kScaleLevels; ++i) tab_base[i + 1] = tab_base[i] + codec_offset_res(i) + 1;
+  const int nt = tab_base[kScaleLevels];
   TableSet& Y = cd->y;
   Y.off.resize(nt); Y.len.resize(nt); Y.sym_min.resize(nt);
   int total = 0, maxL = 0;
-  for (int t = 0; t < nt; ++t) {
-    const int R = codec_radius(codec_scale(t / kMeanOffsets)), L = 2 * R + 1;
-    Y.off[t] = total; Y.len[t] = L; Y.sym_min[t] = -R;
-    total += L + 2;
-    if (L > maxL) maxL = L;
-  }
+  for (int i = 0; i < kScaleLevels; ++i)
+    for (int t = tab_base[i]; t < tab_base[i + 1]; ++t) {
+      const int R = codec_radius(codec_scale(i)), L = 2 * R + 1;
+      Y.off[t] = total; Y.len[t] = L; Y.sym_min[t] = -R;
+      total += L + 2;
+      if (L > maxL) maxL = L;
+    }
   Y.cdf.resize(total);
   int* d_off = nullptr; uint32_t* d_cdf = nullptr; double* d_scr = nullptr;
+  SGA_CUDA(cudaMalloc(&cd->d_tab_base, (kScaleLevels + 1) * sizeof(int)));
+  SGA_CUDA(cudaMemcpyAsync(cd->d_tab_base, tab_base, (kScaleLevels + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   SGA_CUDA(cudaMalloc(&d_off, nt * sizeof(int)));
   SGA_CUDA(cudaMalloc(&d_cdf, static_cast<size_t>(total) * sizeof(uint32_t)));
   SGA_CUDA(cudaMalloc(&d_scr, static_cast<size_t>(nt) * maxL * sizeof(double)));
   SGA_CUDA(cudaMemcpyAsync(d_off, Y.off.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
-  k_gauss_tables<<<nt, 128, 0, st>>>(d_off, d_cdf, d_scr, maxL);
+  k_gauss_tables<<<nt, 128, 0, st>>>(cd->d_tab_base, d_off, d_cdf, d_scr, maxL);
   SGA_LAUNCH_CHECK();
   SGA_CUDA(cudaMemcpyAsync(Y.cdf.data(), d_cdf, static_cast<size_t>(total) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   // ---- factorised-prior tables
@@ -358,11 +372,13 @@ int codec_build_tables(const float* eb_pack, int C, sga_codec* cd, cudaStream_t 
 sga_codec* codec_new() { return new sga_codec(); }
 int codec_num_channels(const sga_codec* cd) { return cd ? cd->C : 0; }
 
-int launch_bin_y(const float* y, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C, int mode, int* tab, int* sym,
-                 float* base, float* yhat, cudaStream_t st) {
+int launch_bin_y(const sga_codec* cd, const float* y, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C, int mode,
+                 int* tab, int* sym, float* base, float* yhat, cudaStream_t st) {
   const long long numel = static_cast<long long>(N) * Hy * Wy * C;
   if (numel <= 0) return SGA_OK;
-  k_bin_y<<<static_cast<unsigned>((numel + 255) / 256), 256, 0, st>>>(y, h2, N, Hy, Wy, Hh, Wh, C, mode, tab, sym, base, yhat);
+  SGA_CHECK(cd->d_tab_base != nullptr, "codec has no device tables (host-only codec)");
+  k_bin_y<<<static_cast<unsigned>((numel + 255) / 256), 256, 0, st>>>(y, h2, N, Hy, Wy, Hh, Wh, C, mode, cd->d_tab_base, tab, sym,
+                                                                       base, yhat);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -389,6 +405,7 @@ int sga_codec_z_centers(const sga_codec* cd, int32_t* out, int32_t n) {
 int sga_codec_destroy(sga_codec* cd) {
   if (!cd) return SGA_OK;
   if (cd->d_center) cudaFree(cd->d_center);
+  if (cd->d_tab_base) cudaFree(cd->d_tab_base);
   delete cd;
   return SGA_OK;
 }

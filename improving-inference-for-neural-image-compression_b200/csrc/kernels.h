@@ -68,8 +68,8 @@ namespace sga {
 int codec_build_tables(const float* eb_pack, int C, sga_codec* cd, cudaStream_t st);
 sga_codec* codec_new();
 // y may be nullptr (decoder side: only the table index and the base of every element are produced)
-int launch_bin_y(const float* y, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C, int mode, int* tab, int* sym,
-                 float* base, float* yhat, cudaStream_t st);
+int launch_bin_y(const sga_codec* cd, const float* y, const float* h2, int N, int Hy, int Wy, int Hh, int Wh, int C, int mode,
+                 int* tab, int* sym, float* base, float* yhat, cudaStream_t st);
 int launch_bin_z(const float* z, long long numel, int C, const sga_codec* cd, int* tab, int* sym, cudaStream_t st);
 int codec_num_channels(const sga_codec* cd);
 

@@ -40,7 +40,7 @@ struct alignas(64) L3FwdParams {
   float grad_scale;
   int N, Hin, Win, C, H, W;
   int tiles_h, tiles_w, total_tiles, kchunks;
-  int prefetch;       // L2 prefetch distance in tiles (env SGA_L3_PREFETCH, default 3)
+  int prefetch;       // L2 prefetch distance in tiles (env SGA_L3_PREFETCH, default 0 = off)
   int stages;         // A-tile ring depth
 };
 
@@ -433,7 +433,7 @@ struct alignas(64) L3DgradFusedParams {
   __nv_bfloat16* out;          // d loss / d x_2
   int N, Hin, Win, C;
   int tiles_h, tiles_w, total_tiles;
-  int prefetch;                // L2 prefetch distance of the x / s tiles, in tiles (env SGA_L3_PREFETCH, default 1; 0 = off)
+  int prefetch;                // L2 prefetch distance of the x / s tiles, in tiles (env SGA_L3_PREFETCH, default 0 = off)
 };
 
 __device__ __forceinline__ float l3_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -844,7 +844,8 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     if (F.stages > kL3MaxStages) F.stages = kL3MaxStages;
     if (const char* e = getenv("SGA_L3_STAGES")) { const int v = atoi(e); if (v >= 2 && v < F.stages) F.stages = v; }
     SGA_CHECK(F.stages >= 2, "not enough shared memory for the layer-3 pipeline");
-    { const char* e = getenv("SGA_L3_PREFETCH"); F.prefetch = e ? atoi(e) : 3; }
+    // measured (profiles/r2_schedule_ab.md): neither the L2 prefetch nor a deeper ring changes the kernel's time
+    { const char* e = getenv("SGA_L3_PREFETCH"); F.prefetch = e ? atoi(e) : 0; }
     c->f_smem = f_fixed + F.stages * 16384;
     c->f_grid = F.total_tiles < sms ? F.total_tiles : sms;
   }
@@ -860,7 +861,7 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     L3DgradFusedParams& DF = c->DF;
     DF.N = N; DF.Hin = Hin; DF.Win = Win; DF.C = C; DF.wpack = w_gather;
     DF.tiles_h = D.tiles_h; DF.tiles_w = D.tiles_w; DF.total_tiles = D.total_tiles;
-    { const char* e = getenv("SGA_L3_PREFETCH"); DF.prefetch = e ? (atoi(e) > 0 ? 1 : 0) : 1; }
+    { const char* e = getenv("SGA_L3_PREFETCH"); DF.prefetch = e ? (atoi(e) > 0 ? 1 : 0) : 0; }
     c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr && x_saved != nullptr && s_saved != nullptr;
     if (c->fused_ok) {
       const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
