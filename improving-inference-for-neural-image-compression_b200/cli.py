@@ -36,6 +36,11 @@ def parse_args(argv, bb=False):
     if bb:
         c.add_argument("--rate_its", type=int, default=2000,
                        help="(new) iterations of the second, rate-only loop (bb_sga.py hard-codes r_opt_its = 2000).")
+    if not bb:
+        c.add_argument("--save_opt_record", action="store_true",
+                       help="(new flag for configs.save_opt_record) log every 10 iterations and write opt-*.npz (sga.py:188-189, 271-278).")
+        c.add_argument("--save_reconstruction", action="store_true",
+                       help="(new flag for sga.py's save_reconstruction) write recon-*.png of a single-image input (sga.py:280-291).")
     c.add_argument("--operand", choices=["bf16", "f32"], default="bf16",
                    help="(new) arithmetic of the (de)conv stacks inside the loop; init and final eval are always f32.")
     c.add_argument("runname", help="Model name identifier, like 'mbt2018-num_filters=192-lmbda=0.01'")
@@ -93,7 +98,12 @@ def compress(args, out=print):
         jobs.append(dict(seg=sg, eng=eng, x=x, st=eng.new_state(y, z)))
     its = args.sga_its
     temps = [annealed_temperature(it, r=args.annealing_rate, ub=0.5, scheme="exp0", t0=args.t0) for it in range(its)]
-    log_points = [it for it in range(its) if it % 100 == 0 or it + 1 == its]                          # sga.py:216
+    from . import configs
+    save_opt_record = bool(getattr(args, "save_opt_record", False) or configs.save_opt_record)
+    save_reconstruction = bool(getattr(args, "save_reconstruction", False) or configs.save_reconstruction)
+    log_itv = 10 if save_opt_record else 100                                                         # sga.py:187-189
+    log_points = [it for it in range(its) if it % log_itv == 0 or it + 1 == its]                      # sga.py:216
+    opt_records = [dict(its=[], T=[], rd_loss=[], rd_loss_after_rounding=[]) for _ in batches]       # sga.py:209
     nb = len(batches)
     nf = 7 if args.verbose else 4
     lines = [[] for _ in batches]
@@ -122,6 +132,9 @@ def compress(args, out=print):
             if not np.isfinite(tot[b]).all():
                 raise FloatingPointError("non-finite SGA statistics at iteration %d of batch %d: %s" % (end, b, line))
             lines[b].append(line)
+            opt_records[b]["its"].append(end); opt_records[b]["T"].append(temps[end]); opt_records[b]["rd_loss"].append(tot[b, 0])
+            if args.verbose:
+                opt_records[b]["rd_loss_after_rounding"].append(tot[b, 4])                           # sga.py:230-236
         first = end + 1
     loop_ms = None
     if t_loop:
@@ -136,9 +149,13 @@ def compress(args, out=print):
     rows = []
     for j in jobs:                                             # sga.py:240-247
         ev = j["eng"].eval_hard(j["x"], j["st"]["y"], j["st"]["z"])
-        ms = msssim_per_image(j["eng"].reconstruction(), j["x"])
+        recon = j["eng"].reconstruction()
+        ms = msssim_per_image(recon, j["x"])
         rows.append(np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
                               ev["est_y_bpp"], ev["est_z_bpp"]], axis=1).astype(np.float32))
+        if save_reconstruction:                               # sga.py:280-291 (single-image inputs only)
+            assert num_images == 1
+            j["recon_u8"] = torch.round(torch.clamp(recon[0], 0, 1) * 255).to(torch.uint8).cpu().numpy()   # utils.write_png
         j["eng"].close()
     rows = np.concatenate(rows, axis=0) if rows else np.zeros((0, 7), dtype=np.float32)
     full = D.gather_rows(rows, num_images, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
@@ -156,6 +173,19 @@ def compress(args, out=print):
     if SCRIPT_NAME != trained_script_name:                    # sga.py:263-268
         save_file = "rd-%s-lmbda=%g+%s-input=%s.npz" % (SCRIPT_NAME, args.lmbda, args.runname, input_file)
     np.savez(os.path.join(args.results_dir, save_file), **results)
+    if save_opt_record:                                       # sga.py:271-278 (the record of the last batch, as in the reference)
+        opt_file = "opt-%s-input=%s.npz" % (args.runname, input_file)
+        if SCRIPT_NAME != trained_script_name:
+            opt_file = "opt-%s-lmbda=%g+%s-input=%s.npz" % (SCRIPT_NAME, args.lmbda, args.runname, input_file)
+        np.savez(os.path.join(args.results_dir, opt_file), **{k: np.asarray(v) for k, v in opt_records[-1].items()})
+    if save_reconstruction and jobs and "recon_u8" in jobs[0]:
+        png = "recon-%s-input=%s.png" % (args.runname, input_file)
+        if SCRIPT_NAME != trained_script_name:
+            png = "recon-%s-lmbda=%g-rd_opt_its=%d+%s-input=%s.png" % (SCRIPT_NAME, args.lmbda, its, args.runname, input_file)
+        png = os.path.join(args.results_dir, png)
+        say("Saving image reconstruction to ", png)
+        from PIL import Image
+        Image.fromarray(jobs[0]["recon_u8"]).save(png)
     for k in EVAL_FIELDS:
         say("Avg {}: {:0.4f}".format(k, results[k].mean()))   # sga.py:293-295
     return results
@@ -183,16 +213,20 @@ def compress_bb(args, out=print):
     W = Wm.load_checkpoint(args.checkpoint_dir, args.runname, args.num_filters, bb=True)
     results = {k: [] for k in BB_EVAL_FIELDS}
     log_points = lambda its: [it for it in range(its) if it % 100 == 0 or it + 1 == its]
-    for (b_lo, b_hi) in D.reference_batches(num_images, H * Wd):
+    for b_idx, (b_lo, b_hi) in enumerate(D.reference_batches(num_images, H * Wd)):
         n_ref = b_hi - b_lo
         lo, hi = D.shard_range(n_ref, rank, ws)
         n_loc = hi - lo
         rows = np.zeros((0, 8), dtype=np.float32)
         say("----RD Optimization----")                        # bb_sga.py:202
 
-        def log(it, T, s):                                    # bb_sga.py:231-232
-            tot = D.allreduce_scalars([s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())])
-            say("it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (it, T, tot[0], tot[1], tot[2], tot[3] / n_ref))
+        def log(it, T, s, extra=None):                        # bb_sga.py:216-232
+            tot = D.allreduce_scalars([s["rd_loss"], s["train_mse"], s["train_bpp"], float(s["psnr"].sum())]
+                                      + ([extra["rd_loss"], extra["train_bpp"], float(extra["psnr"].sum())] if extra else []))
+            line = "it=%d, T=%.3f rd_loss=%.4f mse=%.3f bpp=%.4f psnr=%.4f" % (it, T, tot[0], tot[1], tot[2], tot[3] / n_ref)
+            if extra:
+                line += "\t after rounding: rd_loss=%.4f, bpp=%.4f psnr=%.4f" % (tot[4], tot[5], tot[6] / n_ref)
+            say(line)
 
         def log_rate(it, s):                                  # bb_sga.py:254-255
             if it == 0:
@@ -201,18 +235,19 @@ def compress_bb(args, out=print):
             say("it=", it, "\trate=", D.allreduce_scalars([s["train_bpp"]])[0])
 
         if n_loc > 0:
-            eng = BbEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref, operand=args.operand, seed=0,
+            # Philox key = batch index: every image of the input gets its own noise (the reference's stream keeps advancing)
+            eng = BbEngine(W, n_loc, H, Wd, args.num_filters, args.lmbda, n_ref=n_ref, operand=args.operand, seed=b_idx,
                            first_image=lo)
             x = torch.from_numpy(X[b_lo + lo:b_lo + hi].astype(np.float32) / 255.0).cuda()
             y_tilde, zm, zl, ev = eng.run(x, its=args.sga_its, r_its=args.rate_its, annealing_rate=args.annealing_rate,
-                                          t0=args.t0, log=log, log_rate=log_rate)
+                                          t0=args.t0, log=log, log_rate=log_rate, verbose=args.verbose)
             ms = msssim_per_image(eng.reconstruction(), x)
             rows = np.stack([ev["mse"], ev["psnr"], ms, -10 * np.log10(np.maximum(1 - ms, 1e-12)), ev["est_bpp"],
                              ev["est_y_bpp"], ev["est_z_bpp"], ev["est_bpp_back"]], axis=1).astype(np.float32)
             eng.close()
         elif ws > 1:                                          # ranks without images still join the log all-reduces
             for _ in log_points(args.sga_its):
-                D.allreduce_scalars([0.0] * 4)
+                D.allreduce_scalars([0.0] * (7 if args.verbose else 4))
             for _ in log_points(args.rate_its):
                 D.allreduce_scalars([0.0])
         say()

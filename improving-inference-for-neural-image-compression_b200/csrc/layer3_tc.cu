@@ -22,7 +22,13 @@ using namespace tc;
 // =====================================================================================================
 // forward
 // =====================================================================================================
-constexpr int kL3Threads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue of even / odd tiles
+// warp 0 TMA, warp 1 MMA, warps 2-9 / 10-17 epilogue of even / odd tiles.  The kernel's time is a fixed number of SM cycles
+// (ncu: 448 k cycles whatever the DRAM state; L2 prefetch and ring depth change nothing), set by the epilogue's dependent
+// instruction chains (~780 instructions per warp and tile at 36 % issue utilisation with 4 warps per group), so each group
+// has 8 warps: two per TMEM lane quarter, splitting the accumulator columns and the tile's output pixels.
+constexpr int kL3GroupWarps = 8;
+constexpr int kL3GroupThreads = 32 * kL3GroupWarps;
+constexpr int kL3Threads = 64 + 2 * kL3GroupThreads;
 constexpr int kL3MaxStages = 8;       // the ring takes what shared memory is left (7 stages at C = 192, 6 at C = 256)
 constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
     tma_prefetch_desc(&P.bmap);
     mbar_init(bar_b, 1);
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kL3GroupWarps); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(s_tmem), 256); tmem_relinquish(); }
@@ -131,13 +137,14 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   } else {
     // Two epilogue groups of 4 warps: group g drains the tiles with (it & 1) == g, i.e. TMEM / P buffer g.  The x
     // values of a thread's output pixels are fetched one tile ahead (the col2im loop is otherwise bound by that latency).
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) / kL3GroupWarps;
+    const int half = ((warp - 2) % kL3GroupWarps) >> 2;     // which of the two warps of this quarter: columns [0,48) / [48,80)
     const int row = q * 32 + lane;
-    const int et = (threadIdx.x - 64) & 127;   // 0..127 inside the group
+    const int et = (threadIdx.x - 64) % kL3GroupThreads;    // 0..255 inside the group
     const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
     constexpr int kPix = 2 * kL3IntH * 2 * kL3IntW;         // 336 output pixels per tile
-    constexpr int kPer = (kPix + 127) / 128;                // 3 per thread
+    constexpr int kPer = (kPix + kL3GroupThreads - 1) / kL3GroupThreads;   // 2 per thread
     float acc_s = 0.0f, acc_r = 0.0f;
     int acc_img = -1;
     auto flush = [&]() {
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
-        const int p = et + k * 128;
+        const int p = et + k * kL3GroupThreads;
         const int oy = 2 * hi0 + p / (2 * kL3IntW), ox = 2 * wi0 + p % (2 * kL3IntW);
         const bool in = (p < kPix) && (oy < P.H) && (ox < P.W);
         const float* xp = P.x + ((static_cast<long long>(img) * P.H + oy) * P.W + ox) * 3;
@@ -180,29 +187,29 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
-      {
-        uint32_t r[32];
+      if (half == 0) {                        // columns [0, 48)
+        uint32_t r[32], r2[16];
         tmem_ld32(taddr, r);
+        tmem_ld16(taddr + 32, r2);
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 32; ++k) Pb[row * kPsStride + k] = __uint_as_float(r[k]);
-        tmem_ld32(taddr + 32, r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 32 + k] = __uint_as_float(r2[k]);
+      } else {                                // columns [48, 80)
+        uint32_t r[32];
+        tmem_ld32(taddr + 48, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + 32 + k] = __uint_as_float(r[k]);
-        uint32_t r2[16];
-        tmem_ld16(taddr + 64, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 64 + k] = __uint_as_float(r2[k]);
+        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + 48 + k] = __uint_as_float(r[k]);
       }
       tcgen05_fence_before();
-      named_bar_sync(1 + grp, 128);           // all 128 rows of P are in shared memory; TMEM buffer drained
+      named_bar_sync(1 + grp, kL3GroupThreads);   // all 128 rows of P are in shared memory; TMEM buffer drained
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       // ---- col2im + distortion: 12 x 28 output pixels of this tile's interior
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
-        const int p = et + k * 128;
+        const int p = et + k * kL3GroupThreads;
         if (p >= kPix) continue;
         const int ry = p / (2 * kL3IntW), rx = p % (2 * kL3IntW);
         const int oy = 2 * hi0 + ry, ox = 2 * wi0 + rx;
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
         }
         if (P.gx) *reinterpret_cast<uint2*>(P.gx + opix * 4) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, 0.0f));
       }
-      named_bar_sync(1 + grp, 128);           // P buffer may be overwritten by this group's next tile
+      named_bar_sync(1 + grp, kL3GroupThreads);   // P buffer may be overwritten by this group's next tile
     }
     flush();
   }

@@ -255,7 +255,7 @@ class BbEngine(SgaEngine):
                     est_bpp=per[:, 1] + per[:, 2] - per[:, 5], sse=per[:, 3].copy(), mse=per[:, 4].copy())
 
     def run(self, x, its=2000, r_its=2000, annealing_rate=1e-3, t0=700, T_ub=0.5, rd_lr=0.005, r_lr=0.003, log_itv=100,
-            log=None, log_rate=None):
+            log=None, log_rate=None, verbose=False):
         """The body of bb_sga.py:200-273 for one batch. Returns (y_tilde, z_mean, z_logvar, eval dict)."""
         # 1. R-D optimisation conditioned on x (bb_sga.py:201-233)
         y = self.encode_init(x)
@@ -266,7 +266,10 @@ class BbEngine(SgaEngine):
             at_log = log is not None and (it % log_itv == 0 or it + 1 == its)
             self.step(x, st, T, it, rd_lr, want_stats=at_log)
             if at_log:
-                log(it, T, self.unpack_stats(self.stats.cpu().numpy()))
+                s = self.unpack_stats(self.stats.cpu().numpy())
+                # --verbose (bb_sga.py:218-230): the same statistics with y_tilde = round(y) and the current posterior of z
+                extra = self.eval(x, torch.round(st["y"]), st["z_mean"], st["z_logvar"], step=it) if verbose else None
+                log(it, T, s, extra)
         # 2. y_tilde fixed, rate optimisation w.r.t. z_mean, z_logvar (bb_sga.py:235-256); noise steps continue after
         #    the first loop's so the two loops never share a noise draw
         y_tilde = torch.round(st["y"])                                # np.round: half to even, as torch.round

