@@ -86,53 +86,61 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   const uint32_t tmem_base = *s_tmem;
   const int tiles_per_img = P.tiles_h * P.tiles_w;
 
+  // Issue loops are warp-uniform with one elected lane (as in conv_tc.cu): a single-lane loop makes the compiler wrap every
+  // UTMALDG / UTCHMMA in an election loop with R2UR moves -- hundreds of cycles of dependent-issue latency per K chunk,
+  // which at 3 K chunks per tile is what this kernel's fixed ~2300 cycles per tile were made of.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_b, P.kchunks * b_chunk);
       for (int kc = 0; kc < P.kchunks; ++kc) tma_load_2d(b_base + kc * b_chunk, &P.bmap, bar_b, kc * 64, 0);
-      int stage = 0; uint32_t phase = 0;
-      const int pf = P.prefetch;           // tiles of L2 prefetch distance (0 = off)
-      auto prefetch_tile = [&](int tile) {
-        if (tile >= P.total_tiles) return;
-        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
-        const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+    }
+    int stage = 0; uint32_t phase = 0;
+    const int pf = P.prefetch;           // tiles of L2 prefetch distance (0 = off)
+    auto prefetch_tile = [&](int tile) {
+      if (tile >= P.total_tiles) return;
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+      if (elect_one())
         for (int kc = 0; kc < P.kchunks; ++kc) tma_prefetch_4d(&P.amap, kc * 64, w0, h0, img);
-      };
-      for (int d = 2; d < 2 + pf; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);   // the ring itself runs ~2 tiles ahead
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
-        const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
-        if (pf) prefetch_tile(tile + (2 + pf) * gridDim.x);
-        for (int kc = 0; kc < P.kchunks; ++kc) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+    };
+    for (int d = 2; d < 2 + pf; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);   // the ring itself runs ~2 tiles ahead
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / P.tiles_w) * kL3IntH - 1, w0 = (tt % P.tiles_w) * kL3IntW - 1;
+      if (pf) prefetch_tile(tile + (2 + pf) * gridDim.x);
+      for (int kc = 0; kc < P.kchunks; ++kc) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, 16384);
           tma_load_4d(a_base + stage * 16384, &P.amap, bar_full + 8 * stage, kc * 64, w0, h0, img);
-          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc_bf16(128, kL3NPad);
-      mbar_wait(bar_b, 0);
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+    const uint32_t idesc = instr_desc_bf16(128, kL3NPad);
+    // descriptors: only the 14-bit start-address field changes (stage / K chunk, K = 16 slice), added to a prebuilt base
+    const uint64_t adesc0 = smem_desc_sw128(a_base), bdesc0 = smem_desc_sw128(b_base);
+    mbar_wait(bar_b, 0);
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * 128;
+      for (int kc = 0; kc < P.kchunks; ++kc) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int kc = 0; kc < P.kchunks; ++kc) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + static_cast<uint64_t>((stage * 16384) >> 4);
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>((kc * b_chunk) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(d_tmem, smem_desc_sw128(a_base + stage * 16384 + kk * 32),
-                      smem_desc_sw128(b_base + kc * b_chunk + kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (kc | kk) != 0 ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);
-          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_tfull + 8 * buf);
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(bar_tfull + 8 * buf);
     }
   } else {
     // Two epilogue groups of 4 warps: group g drains the tiles with (it & 1) == g, i.e. TMEM / P buffer g.  The x
@@ -555,64 +563,70 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   constexpr uint32_t kNormCol = NF;
 
   if (warp == 0) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_g, kGammaBytes);
       for (int kc = 0; kc < kKc; ++kc) tma_load_2d(gamma_base + kc * NF * 128, &P.gmap, bar_g, kc * 64, 0);
-      mbar_wait(bar_g, 0);
-      const uint32_t idesc = instr_desc_bf16(128, NF);
-      int it = 0;
-      auto mix = [&](int j) {   // mixing GEMM of tile j: [128 x NF] = t[128 x NF] * gamma^T
-        mbar_wait(bar_a2, j & 1);                     // pass 1 of tile j done: operand in smem, accumulator drained
-        mbar_wait(bar_nempty, (j & 1) ^ 1u);          // pass 2 of tile j-1 has read the previous mixing result
-        tcgen05_fence_after();
+    }
+    mbar_wait(bar_g, 0);
+    const uint32_t idesc = instr_desc_bf16(128, NF);
+    const uint64_t a2desc0 = smem_desc_sw128(a2_base), gdesc0 = smem_desc_sw128(gamma_base);
+    const uint64_t adesc0 = smem_desc_interleave(a_base, 2048, 128), bdesc0 = smem_desc_interleave(b_base, NF * 16, 128);
+    int it = 0;
+    auto mix = [&](int j) {   // mixing GEMM of tile j: [128 x NF] = t[128 x NF] * gamma^T
+      mbar_wait(bar_a2, j & 1);                     // pass 1 of tile j done: operand in smem, accumulator drained
+      mbar_wait(bar_nempty, (j & 1) ^ 1u);          // pass 2 of tile j-1 has read the previous mixing result
+      tcgen05_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kc = 0; kc < kKc; ++kc)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_base + kNormCol, smem_desc_sw128(a2_base + kc * 16384 + kk * 32),
-                      smem_desc_sw128(gamma_base + kc * NF * 128 + kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base + kNormCol, a2desc0 + static_cast<uint64_t>((kc * 16384 + kk * 32) >> 4),
+                      gdesc0 + static_cast<uint64_t>((kc * NF * 128 + kk * 32) >> 4), idesc, (kc | kk) != 0 ? 1u : 0u);
         umma_commit(bar_nfull);
-      };
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
-        mbar_wait(bar_afull, it & 1);
-        tcgen05_fence_after();
+      }
+    };
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
+      mbar_wait(bar_afull, it & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 5; ++ks) {
-          const uint64_t ad = smem_desc_interleave(a_base + ks * 2 * 2048, 2048, 128);
-          const uint64_t bd = smem_desc_interleave(b_base + ks * 2 * (NF * 16), NF * 16, 128);
-          umma_bf16(tmem_base, ad, bd, idesc, ks != 0 ? 1u : 0u);
-        }
+        for (int ks = 0; ks < 5; ++ks)
+          umma_bf16(tmem_base, adesc0 + static_cast<uint64_t>((ks * 2 * 2048) >> 4),
+                    bdesc0 + static_cast<uint64_t>((ks * 2 * (NF * 16)) >> 4), idesc, ks != 0 ? 1u : 0u);
         umma_commit(bar_aempty);
         umma_commit(bar_tfull);
       }
-      if (it > 0) mix(it - 1);
     }
+    if (it > 0) mix(it - 1);
   } else if (warp == 1) {
-    // ===================== TMA producer: saved x and s tiles =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
-        const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
-        if (P.prefetch) {
-          // the x / s buffers are single (shared memory is full), so the loads of tile it+1 can only be issued late in tile
-          // it: pull them into L2 a whole tile earlier
-          const int nt = tile + P.prefetch * static_cast<int>(gridDim.x);
-          if (nt < P.total_tiles) {
-            const int nimg = nt / tiles_per_img, ntt = nt % tiles_per_img;
-            const int nh0 = (ntt / P.tiles_w) * 8, nw0 = (ntt % P.tiles_w) * 16;
-            for (int kc = 0; kc < kKc; ++kc) {
-              tma_prefetch_4d(&P.smap, kc * 64, nw0, nh0, nimg);
-              tma_prefetch_4d(&P.xmap, kc * 64, nw0, nh0, nimg);
-            }
+    // ===================== TMA producer: saved x and s tiles (warp-uniform loop) =====================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
+      if (P.prefetch) {
+        // the x / s buffers are single (shared memory is full), so the loads of tile it+1 can only be issued late in tile
+        // it: pull them into L2 a whole tile earlier (opt-in: measured no gain)
+        const int nt = tile + P.prefetch * static_cast<int>(gridDim.x);
+        if (nt < P.total_tiles && elect_one()) {
+          const int nimg = nt / tiles_per_img, ntt = nt % tiles_per_img;
+          const int nh0 = (ntt / P.tiles_w) * 8, nw0 = (ntt % P.tiles_w) * 16;
+          for (int kc = 0; kc < kKc; ++kc) {
+            tma_prefetch_4d(&P.smap, kc * 64, nw0, nh0, nimg);
+            tma_prefetch_4d(&P.xmap, kc * 64, nw0, nh0, nimg);
           }
         }
-        if (it > 0) mbar_wait(bar_a2, (it - 1) & 1);          // pass 1 of the previous tile has consumed its s tile
+      }
+      if (it > 0) mbar_wait(bar_a2, (it - 1) & 1);          // pass 1 of the previous tile has consumed its s tile
+      if (elect_one()) {
         mbar_arrive_expect_tx(bar_sfull, kTileBytes);
         for (int kc = 0; kc < kKc; ++kc) tma_load_4d(s_base + kc * 16384, &P.smap, bar_sfull, kc * 64, w0, h0, img);
-        if (it > 0) mbar_wait(bar_nfull, (it - 1) & 1);       // the mixing GEMM has finished reading t of the previous tile
+      }
+      if (it > 0) mbar_wait(bar_nfull, (it - 1) & 1);       // the mixing GEMM has finished reading t of the previous tile
+      if (elect_one()) {
         mbar_arrive_expect_tx(bar_xfull, kTileBytes);
         for (int kc = 0; kc < kKc; ++kc) tma_load_4d(a2_base + kc * 16384, &P.xmap, bar_xfull, kc * 64, w0, h0, img);
       }
