@@ -397,7 +397,8 @@ def main_ours(args, rank, ws, local, wl):
         flops_iter += tot
         for k, v in layer3_bytes(j["n"], H, Wd, C).items():
             l3b[k] += v
-    fused = C in (64, 128, 192)
+    fused = C in (64, 128, 192, 256)
+    l3_fused = C in (64, 128, 192)         # C = 256: the layer-3 dgrad and the IGDN_2 backward are separate launches
     conv_labels = {"hs0_fwd": "hs0", "hs1_fwd": "hs1", "hs2_fwd": "hs2", "hs0_dgrad": "hs0", "hs1_dgrad": "hs1",
                    "hs2_dgrad": "hs2", "gs0_fwd": "gs0", "gs1_fwd": "gs1", "gs2_fwd": "gs2", "gs0_dgrad": "gs0",
                    "gs1_dgrad": "gs1", "gs2_dgrad": "gs2"}
@@ -410,7 +411,10 @@ def main_ours(args, rank, ws, local, wl):
     kfl["l3_dgrad"] = fl["gs3"]
     if fused:
         for k, v in fused_extra.items():
-            kfl[k] += fl[v]
+            if k == "l3_dgrad" and not l3_fused:
+                kfl["igdn_bwd"] = fl[v]
+            else:
+                kfl[k] += fl[v]
     else:
         kfl["igdn_fwd"] = sum(fl["igdn%d" % i] for i in range(3))
         kfl["igdn_bwd"] = kfl["igdn_fwd"]
@@ -447,8 +451,9 @@ def main_ours(args, rank, ws, local, wl):
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
-                     "kernel": ("k_conv_igdn_fwd<%d,2> (g_s layer 2 forward: transposed 5x5 conv + fused inverse GDN), the step's "
-                                "largest launch" % C) if fused else "k_conv_tc (g_s layer 2 forward, un-fused)",
+                     "kernel": ("%s (g_s layer 2 forward: transposed 5x5 conv + fused inverse GDN), the step's largest launch"
+                                % ("k_conv_igdn_fwd<%d,2>" % C if C <= 192 else "k_conv_tc<1,256,4,2>")) if fused
+                               else "k_conv_tc (g_s layer 2 forward, un-fused)",
                      "achieved": dom_row.get("achieved"), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": dom_row.get("frac"),
                      "traffic": dom_row.get("traffic"),
                      "traffic_source": TRAFFIC_FILE if dom_row.get("traffic") is not None else None,

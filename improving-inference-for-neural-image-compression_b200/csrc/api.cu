@@ -162,6 +162,10 @@ static void compute_dims(const sga_config& c, Dims& d) {
   d.nz = static_cast<long long>(d.N) * d.Hz * d.Wz * d.C;
 }
 
+// the layer-3 dgrad can carry the IGDN_2 backward in its epilogue only while gamma (C x C) and a saved x / s tile pair fit
+// in shared memory beside the gather operands: C <= 192 (layer3_tc.cu)
+static bool l3_fusable(int C) { return C == 64 || C == 128 || C == 192; }
+
 static long long gs_elems(const Dims& d, int level) {  // level 1..3: output of g_s layer level-1
   return static_cast<long long>(d.N) * d.Hs[level] * d.Ws[level] * d.C;
 }
@@ -356,7 +360,12 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
     if (c->fused) {
       // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
       // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
-      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
+      if (l3_fusable(d.C)) {
+        PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
+      } else {
+        PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
+        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_act[2], c->b_s[2], c->b_gb[2], st, 1));
+      }
       PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
       PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
       PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
@@ -454,7 +463,12 @@ static int step_bf16(sga_ctx* c, const float* x, const float* y, const float* z,
     if (c->fused) {
       // every IGDN backward runs in the epilogue of the dgrad that produces its upstream gradient: IGDN_2 inside the
       // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
-      PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
+      if (l3_fusable(d.C)) {
+        PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
+      } else {   // C = 256: x_2 = act_2 / s_2 inside the stand-alone IGDN backward
+        PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
+        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_act[2], c->b_s[2], c->b_gb[2], st, 1));
+      }
       PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
       PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
       PROF(c, SGA_PROF_CONV_GS + 3, st, tc_conv_launch(c->tc_gs_d[0], nullptr, 0, nullptr, nullptr, c->gy_dist, st));
@@ -586,6 +600,7 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
       for (int i = 0; i < 3; ++i) {
         R(&c->b_s[i], gs_elems(d, i + 1)); R(&c->b_act[i], gs_elems(d, i + 1)); R(&c->b_gb[i], gs_elems(d, i + 1));
         if (!c->fused) { R(&c->b_xpre[i], gs_elems(d, i + 1)); R(&c->b_ga[i], gs_elems(d, i + 1)); }
+        else if (i == 2 && !l3_fusable(d.C)) R(&c->b_ga[2], gs_elems(d, 3));   // C = 256: layer-3 dgrad + IGDN_2 backward stay apart
       }
       R(&c->b_gx4, static_cast<long long>(d.N) * d.Hs[4] * d.Ws[4] * 4);
       R(&c->b_gh1, nh1); R(&c->b_gh0, nh0);
@@ -702,10 +717,12 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
         SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
       }
     }
+    if (c->fused && !l3_fusable(C))
+      SGA_TRY(igdn_tc_create(c->gs_gamma_b[2], C, static_cast<long long>(d.N) * d.Hs[3] * d.Ws[3], 1, &c->ig_b[2]));
     SGA_TRY(c->alloc(&c->l3_wscatter, 80 * C)); SGA_TRY(c->alloc(&c->l3_wgather, 80 * C));
     SGA_TRY(l3_pack_weights(c->gs[3].w, C, c->l3_wscatter, c->l3_wgather, st));
     // fused: the IGDN backward recovers x_2 from the saved act_2 and s_2 (the fused forward does not store x)
-    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, c->fused ? c->gs_gamma_b[2] : nullptr,
+    SGA_TRY(l3_tc_create(c->b_act[2], c->l3_wscatter, c->l3_wgather, (c->fused && l3_fusable(C)) ? c->gs_gamma_b[2] : nullptr,
                          c->fused ? c->b_act[2] : c->b_xpre[2], c->b_s[2], d.N, d.Hs[3], d.Ws[3], C, d.H, d.W, &c->l3));
     SGA_CUDA(cudaStreamSynchronize(st));
   }

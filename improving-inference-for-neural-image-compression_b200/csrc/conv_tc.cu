@@ -92,7 +92,13 @@ template <int FUSE, int NF, int G, int CG>
 __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_constant__ TcParams P) {
   static_assert(FUSE == 0 || G * 64 == NF, "fused variants: one 32-column chunk per warp and half");
   static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
-  static_assert(FUSE == 0 || FUSE == 2, "the forward fusion lives in conv_igdn_fwd_tc.cu");
+  // FUSE == 1 (two-pass forward fusion) is only instantiated for NF = 256, where the split-warp kernel of
+  // conv_igdn_fwd_tc.cu does not fit in TMEM (2 x 256 accumulator columns leave no room for the mixing result)
+  static_assert(FUSE != 1 || NF == 256, "the forward fusion of NF <= 192 lives in conv_igdn_fwd_tc.cu");
+  // accumulator buffers: two (the epilogue of tile i overlaps the MMAs of tile i+1) unless 2*NF + NF/2 > 512 TMEM
+  // columns -- NF = 256: one accumulator + the N/2-column mixing result = 384 columns; the accumulator is released after
+  // pass 1 (its content lives on in registers as packed bf16), so the tensor pipe only idles during pass 1
+  constexpr int kNBuf = (FUSE != 0 && 2 * NF + NF / 2 > kTmemCols) ? 1 : 2;
   pdl_launch_dependents();
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kAccStride = (FUSE != 0) ? NF : 256;               // TMEM columns between the two accumulators
-  constexpr int kNormCol = 2 * NF;                                 // fused: mixing result (N/2 columns)
+  constexpr int kNormCol = kNBuf * NF;                             // fused: mixing result (N/2 columns)
   constexpr int kNHalf = NF / 2;
 
   for (int i = threadIdx.x; i < P.Nn && i < 256; i += blockDim.x) {
@@ -134,6 +140,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   }
   if (FUSE == 0)
     for (int i = 256 + threadIdx.x; i < P.Nn && i < 512; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
+  if (FUSE == 1)
+    for (int i = threadIdx.x; i < NF; i += blockDim.x) s_bias[256 + i] = P.beta[i];
 
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < kMaxViews; ++v) tma_prefetch_desc(&P.amap[v]);
@@ -279,8 +287,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
         if (!decode_slot<CG>(P, w, rank, tc_)) continue;
         const int nk = P.job[tc_.job].ntaps * P.kchunks;
         const int ins0 = (P.mix_at0 * nk) / 8, ins1 = (P.mix_at1 * nk) / 8 < nk ? (P.mix_at1 * nk) / 8 : nk - 1;
-        const int buf = it & 1;
-        SGA_TIMED(1, wait_x(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u));
+        const int buf = it % kNBuf;
+        SGA_TIMED(1, wait_x(bar_tempty + 8 * buf, ((it / kNBuf) & 1) ^ 1u));
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int k = 0; k < nk; ++k) {
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
       TileCoord tc_;
       if (!decode_slot<CG>(P, w, rank, tc_)) continue;
       const TcJob& J = P.job[tc_.job];
-      const int buf = it & 1;
+      const int buf = it % kNBuf;
       const int i = tc_.h0 + row / P.TW, j = tc_.w0 + row % P.TW;
       const bool valid = (i < J.Ho) && (j < J.Wo) && (tc_.img < P.N);
       const long long off0 = J.out_off + tc_.img * P.oN + i * J.oH + j * J.oW + tc_.n0;
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           }
         }
       }
-      SGA_TIMED(0, mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1));
+      SGA_TIMED(0, mbar_wait(bar_tfull + 8 * buf, (it / kNBuf) & 1));
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + lane_off;
       if (FUSE == 0) {
@@ -376,7 +384,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           uint32_t a2w[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+            if (FUSE == 1) {
+              // forward: x = acc + bias kept as packed bf16; the mixing sees the square of that stored x
+              v0 += s_bias[c * 32 + 2 * e];
+              v1 += s_bias[c * 32 + 2 * e + 1];
+              const uint32_t xb = pack_bf16(v0, v1);
+              keep[h][e] = xb;
+              const float x0 = bf16_lo(xb), x1 = bf16_hi(xb);
+              a2w[e] = pack_bf16(x0 * x0, x1 * x1);
+              continue;
+            }
             // the forward stores act = x*s and s: x = act / s
             const uint32_t aw = xin[h][e];
             const uint32_t sw = sin[h][e];
@@ -415,12 +433,29 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
           if (lane == 0) arrive_lead(bar_nempty, lead_nempty);   // the mixing result is in registers: release the TMEM region
           ++halves;
           uint32_t o[16];
+          if (FUSE == 1) {
+            // s = sqrt(beta + x^2 @ gamma) stored as bf16; act = x * (stored s), so that the backward's x = act / s inverts it
+            uint32_t so[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
-            const uint32_t kw = keep[h][e];
-            const uint32_t xw = xin[h][e];
-            o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
+            for (int e = 0; e < 16; ++e) {
+              const float s0 = fast_sqrt(__uint_as_float(r[2 * e]) + s_bias[256 + c * 32 + 2 * e]);
+              const float s1 = fast_sqrt(__uint_as_float(r[2 * e + 1]) + s_bias[256 + c * 32 + 2 * e + 1]);
+              so[e] = pack_bf16(s0, s1);
+              const uint32_t kw = keep[h][e];
+              o[e] = pack_bf16(bf16_lo(kw) * bf16_lo(so[e]), bf16_hi(kw) * bf16_hi(so[e]));
+            }
+            if (valid) {
+              st_global_v8(P.s_out + off0 + c * 32, &so[0]);
+              st_global_v8(P.s_out + off0 + c * 32 + 16, &so[8]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float m0 = __uint_as_float(r[2 * e]), m1 = __uint_as_float(r[2 * e + 1]);
+              const uint32_t kw = keep[h][e];
+              const uint32_t xw = xin[h][e];
+              o[e] = pack_bf16(bf16_lo(kw) + bf16_lo(xw) * m0, bf16_hi(kw) + bf16_hi(xw) * m1);
+            }
           }
           if (valid) {
             st_global_v8(P.out_bf16 + off0 + c * 32, &o[0]);
@@ -495,6 +530,8 @@ typedef void (*TcKernel)(const TcParams);
 template <int CG>
 static TcKernel select_kernel_cg(int fuse, int nf) {
   if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups, CG>;
+  if (fuse == 1) return k_conv_tc<1, 256, 4, CG>;          // two-pass forward fusion: NF = 256 only
+  if (nf == 256) return k_conv_tc<2, 256, 4, CG>;
   return nf == 192 ? k_conv_tc<2, 192, 3, CG> : (nf == 128 ? k_conv_tc<2, 128, 2, CG> : k_conv_tc<2, 64, 1, CG>);
 }
 static TcKernel select_kernel(int fuse, int nf, int cg) {
@@ -529,14 +566,16 @@ static int launch_tc(const TcConv* c, const TcParams& P, cudaStream_t st) {
   return SGA_OK;
 }
 
-bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192; }
+bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192 || cout == 256; }
+// NF = 256 does not fit the split-warp forward kernel (TMEM): its forward fusion is the two-pass epilogue of k_conv_tc
+static bool fwd_two_pass(int cout) { return cout == 256; }
 
 int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, int fuse,
                    const __nv_bfloat16* mix_op, TcConv** out) {
   const ConvGeom& g = plan.g;
   SGA_CHECK(g.Cin % 8 == 0, "tcgen05 conv needs Cin %% 8 == 0 (got %d)", g.Cin);
   SGA_CHECK(g.Cout % 16 == 0 && g.Cout <= 512, "tcgen05 conv needs Cout %% 16 == 0 and <= 512 (got %d)", g.Cout);
-  SGA_CHECK(fuse == 0 || (tc_conv_can_fuse(g.Cout) && mix_op != nullptr), "IGDN fusion needs Cout in {64,128,192}");
+  SGA_CHECK(fuse == 0 || (tc_conv_can_fuse(g.Cout) && mix_op != nullptr), "IGDN fusion needs Cout in {64,128,192,256}");
   for (int jn = 1; jn < plan.njobs; ++jn)
     SGA_CHECK(plan.job[jn].Ho == plan.job[0].Ho && plan.job[jn].Wo == plan.job[0].Wo, "jobs of a plan must share a grid");
   TcConv* c = new TcConv();
@@ -551,6 +590,9 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   {
     const char* e0 = getenv("SGA_MIX_AT0"); const char* e1 = getenv("SGA_MIX_AT1");
     P.mix_at0 = e0 ? atoi(e0) : 6; P.mix_at1 = e1 ? atoi(e1) : 8;
+    // one accumulator buffer (NF = 256): the epilogue warps must finish pass 2 of tile i-1 before they can drain tile i,
+    // and tile i+1 cannot start before that -- issue the mixing GEMM of tile i-1 at the very start of tile i's main loop
+    if (fuse != 0 && g.Cout == 256 && !e0 && !e1) { P.mix_at0 = 0; P.mix_at1 = 1; }
     const char* ed = getenv("SGA_DBG");
     P.dbg = ed ? atoi(ed) : 0;
   }
@@ -588,7 +630,8 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
   P.spread = (sp_units * P.n_tiles_n < ctas && getenv("SGA_NO_SMALL") == nullptr) ? 1 : 0;
   const int b_bytes = (P.block_n / c->cg) * kBlockK * 2;
   const int a2_bytes = fuse ? (g.Cout / 64) * kABytes : 0;
-  const int fixed = (fuse == 1) ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + 512 * 4 + 256;
+  const bool split_fwd = (fuse == 1) && !fwd_two_pass(g.Cout);
+  const int fixed = split_fwd ? igdn_fwd_smem_fixed(g.Cout, c->cg) : 1024 + a2_bytes + 512 * 4 + 256;
   int stages = (227 * 1024 - fixed) / (kABytes + b_bytes);
   P.a_stages = 0;
   if (P.halo) {                                       // halo ring (A) + weight ring (B)
@@ -672,7 +715,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     const uint64_t dims[2] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(g.Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(g.Cout) * 2};
     // backward fusion: halves of the result (N/2 rows per MMA); forward fusion: 64-column parts
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>((fuse == 1 ? 64 : g.Cout / 2) / c->cg)};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>((split_fwd ? 64 : g.Cout / 2) / c->cg)};
     int st = tma_encode_tiled(&P.gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, mix_op, dims, strides, box,
                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
@@ -681,7 +724,7 @@ int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bflo
     const int units = sp_units * P.n_tiles_n * (P.spread ? P.njobs : 1);
     c->grid = c->cg * (units < ctas ? units : ctas);
   }
-  if (fuse == 1) SGA_TRY(igdn_fwd_set_attr(g.Cout, c->cg));
+  if (split_fwd) SGA_TRY(igdn_fwd_set_attr(g.Cout, c->cg));
   else SGA_CUDA(cudaFuncSetAttribute(select_kernel(fuse, g.Cout, c->cg), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return SGA_OK;
@@ -704,6 +747,7 @@ int tc_conv_launch_igdn_fwd(TcConv* c, const float* bias, const float* beta, __n
   if (c->P.n_spatial == 0) return SGA_OK;
   TcParams P = c->P;
   P.bias = bias; P.beta = beta; P.s_out = s_out; P.out_bf16 = act_out;
+  if (fwd_two_pass(P.Nn)) return launch_tc(c, P, st);
   return launch_igdn_fwd_kernel(c, P, st);
 }
 

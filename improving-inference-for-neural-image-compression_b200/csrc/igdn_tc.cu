@@ -28,6 +28,7 @@ struct alignas(64) IgdnParams {
   __nv_bfloat16* s_out;       // forward
   long long pixels;
   int C, block_n, n_tiles_n, bwd;
+  int x_is_act;               // backward: `x` holds the saved activation act = x*s (the fused forward does not store x)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -158,6 +159,10 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
               float gf[8], sf[8];
               unpack8(gv[u], gf);
               unpack8(sv[u], sf);
+              if (P.x_is_act) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xf[e] = xf[e] / sf[e];
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) t[e] = gf[e] * xf[e] / sf[e];
             } else {
@@ -203,6 +208,10 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
               float gf[8], sf[8];
               unpack8(gv[u], gf);
               unpack8(sv[u], sf);
+              if (P.x_is_act) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xf[e] = xf[e] / sf[e];
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = gf[e] * sf[e] + xf[e] * __uint_as_float(r[u * 8 + e]);
               reinterpret_cast<uint4*>(P.out + off)[u] = pack8(o);
@@ -301,10 +310,10 @@ int igdn_tc_forward(const IgdnTc* c, const __nv_bfloat16* x, const float* beta, 
 }
 
 int igdn_tc_backward(const IgdnTc* c, const __nv_bfloat16* g, const __nv_bfloat16* x, const __nv_bfloat16* s,
-                     __nv_bfloat16* gx, cudaStream_t st) {
+                     __nv_bfloat16* gx, cudaStream_t st, int x_is_act) {
   if (c->P.pixels == 0) return SGA_OK;
   IgdnParams P = c->P;
-  P.x = x; P.g = g; P.s = s; P.out = gx;
+  P.x = x; P.g = g; P.s = s; P.out = gx; P.x_is_act = x_is_act;
   k_igdn_tc<<<c->grid, kIgdnThreads, c->smem_bytes, st>>>(P);
   SGA_LAUNCH_CHECK();
   return SGA_OK;

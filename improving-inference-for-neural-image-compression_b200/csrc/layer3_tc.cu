@@ -22,13 +22,15 @@ using namespace tc;
 // =====================================================================================================
 // forward
 // =====================================================================================================
-// warp 0 TMA, warp 1 MMA, warps 2-9 / 10-17 epilogue of even / odd tiles.  The kernel's time is a fixed number of SM cycles
-// (ncu: 448 k cycles whatever the DRAM state; L2 prefetch and ring depth change nothing), set by the epilogue's dependent
-// instruction chains (~780 instructions per warp and tile at 36 % issue utilisation with 4 warps per group), so each group
-// has 8 warps: two per TMEM lane quarter, splitting the accumulator columns and the tile's output pixels.
-constexpr int kL3GroupWarps = 8;
+// warp 0 TMA, warp 1 MMA, then kL3Groups epilogue groups of kL3GroupWarps warps; group g drains the tiles with
+// it % kL3Groups == g (TMEM accumulator g, col2im buffer g).  The kernel's time is a fixed number of SM cycles (ncu: 448 k
+// cycles whatever the DRAM state; L2 prefetch and ring depth change nothing): a tile's epilogue is one dependent chain
+// (accumulator -> registers -> shared memory -> barrier -> overlap-add -> global) of ~4400 cycles whatever the number of warps
+// that share it (8 warps per group: same time as 4), so throughput comes from the number of tiles in flight.
+constexpr int kL3Groups = 3;
+constexpr int kL3GroupWarps = 4;
 constexpr int kL3GroupThreads = 32 * kL3GroupWarps;
-constexpr int kL3Threads = 64 + 2 * kL3GroupThreads;
+constexpr int kL3Threads = 64 + kL3Groups * kL3GroupThreads;
 constexpr int kL3MaxStages = 8;       // the ring takes what shared memory is left (7 stages at C = 192, 6 at C = 256)
 constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
@@ -60,14 +62,14 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   const uint32_t b_base = base;
   const uint32_t a_base = base + P.kchunks * b_chunk;
   uint8_t* p_after = smem + P.kchunks * b_chunk + P.stages * 16384;
-  float* Ps = reinterpret_cast<float*>(p_after);     // [2][128][81]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_after + 2 * 128 * kPsStride * 4);
+  float* Ps = reinterpret_cast<float*>(p_after);     // [kL3Groups][128][81]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_after + kL3Groups * 128 * kPsStride * 4);
   const uint32_t bar_b = smem_u32(bars);
   const uint32_t bar_full = bar_b + 8;
   const uint32_t bar_empty = bar_full + 8 * kL3MaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kL3MaxStages;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kL3MaxStages + 4);
+  const uint32_t bar_tempty = bar_tfull + 8 * kL3Groups;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kL3MaxStages + 2 * kL3Groups);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -75,10 +77,10 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
     tma_prefetch_desc(&P.bmap);
     mbar_init(bar_b, 1);
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kL3GroupWarps); }
+    for (int b = 0; b < kL3Groups; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kL3GroupWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), 512); tmem_relinquish(); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
     mbar_wait(bar_b, 0);
     int stage = 0; uint32_t phase = 0; int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+      const int buf = it % kL3Groups;
+      mbar_wait(bar_tempty + 8 * buf, ((it / kL3Groups) & 1) ^ 1u);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + buf * 128;
       for (int kc = 0; kc < P.kchunks; ++kc) {
@@ -147,12 +149,11 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
     // values of a thread's output pixels are fetched one tile ahead (the col2im loop is otherwise bound by that latency).
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
     const int grp = (warp - 2) / kL3GroupWarps;
-    const int half = ((warp - 2) % kL3GroupWarps) >> 2;     // which of the two warps of this quarter: columns [0,48) / [48,80)
     const int row = q * 32 + lane;
-    const int et = (threadIdx.x - 64) % kL3GroupThreads;    // 0..255 inside the group
+    const int et = (threadIdx.x - 64) % kL3GroupThreads;    // thread index inside the group
     const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
     constexpr int kPix = 2 * kL3IntH * 2 * kL3IntW;         // 336 output pixels per tile
-    constexpr int kPer = (kPix + kL3GroupThreads - 1) / kL3GroupThreads;   // 2 per thread
+    constexpr int kPer = (kPix + kL3GroupThreads - 1) / kL3GroupThreads;   // 3 per thread
     float acc_s = 0.0f, acc_r = 0.0f;
     int acc_img = -1;
     auto flush = [&]() {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
     const int first = blockIdx.x + grp * gridDim.x;
     if (first < P.total_tiles) fetch_x(first);
     int it = grp;
-    for (int tile = first; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
+    for (int tile = first; tile < P.total_tiles; tile += kL3Groups * gridDim.x, it += kL3Groups) {
       const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
       const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
       const int buf = grp;
@@ -190,26 +191,23 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       for (int k = 0; k < kPer; ++k)
 #pragma unroll
         for (int c = 0; c < 3; ++c) xc[k][c] = xn[k][c];
-      if (tile + 2 * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tile + 2 * gridDim.x);
+      if (tile + kL3Groups * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tile + kL3Groups * gridDim.x);
       float* Pb = Ps + buf * 128 * kPsStride;
-      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      mbar_wait(bar_tfull + 8 * buf, (it / kL3Groups) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
-      if (half == 0) {                        // columns [0, 48)
-        uint32_t r[32], r2[16];
+      {
+        uint32_t r[32], r1[32], r2[16];
         tmem_ld32(taddr, r);
-        tmem_ld16(taddr + 32, r2);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld16(taddr + 64, r2);
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 32; ++k) Pb[row * kPsStride + k] = __uint_as_float(r[k]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 32 + k] = __uint_as_float(r2[k]);
-      } else {                                // columns [48, 80)
-        uint32_t r[32];
-        tmem_ld32(taddr + 48, r);
-        tmem_ld_wait();
+        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + 32 + k] = __uint_as_float(r1[k]);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) Pb[row * kPsStride + 48 + k] = __uint_as_float(r[k]);
+        for (int k = 0; k < 16; ++k) Pb[row * kPsStride + 64 + k] = __uint_as_float(r2[k]);
       }
       tcgen05_fence_before();
       named_bar_sync(1 + grp, kL3GroupThreads);   // all 128 rows of P are in shared memory; TMEM buffer drained
@@ -263,7 +261,7 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // =====================================================================================================
@@ -860,7 +858,7 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     st = tma_encode_tiled(&F.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_scatter, bdims, bstr, bbox,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (st != SGA_OK) { delete c; return st; }
-    const int f_fixed = 1024 + F.kchunks * kL3NPad * 128 + 2 * 128 * kPsStride * 4 + 256;
+    const int f_fixed = 1024 + F.kchunks * kL3NPad * 128 + kL3Groups * 128 * kPsStride * 4 + 256;
     F.stages = (227 * 1024 - f_fixed) / 16384;
     if (F.stages > kL3MaxStages) F.stages = kL3MaxStages;
     if (const char* e = getenv("SGA_L3_STAGES")) { const int v = atoi(e); if (v >= 2 && v < F.stages) F.stages = v; }

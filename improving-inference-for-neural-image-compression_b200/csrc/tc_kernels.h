@@ -10,8 +10,9 @@ int igdn_tc_create(const __nv_bfloat16* gamma_op, int C, long long pixels, int b
 void igdn_tc_destroy(IgdnTc* c);
 int igdn_tc_forward(const IgdnTc* c, const __nv_bfloat16* x, const float* beta, __nv_bfloat16* out, __nv_bfloat16* s_out,
                     cudaStream_t st);
+// x_is_act: `x` holds the saved activation act = x*s instead of x (the fused forward kernels do not store x)
 int igdn_tc_backward(const IgdnTc* c, const __nv_bfloat16* g, const __nv_bfloat16* x, const __nv_bfloat16* s,
-                     __nv_bfloat16* gx, cudaStream_t st);
+                     __nv_bfloat16* gx, cudaStream_t st, int x_is_act = 0);
 
 // layer3_tc.cu
 struct L3Tc;
