@@ -29,6 +29,7 @@ struct alignas(64) IgdnParams {
   long long pixels;
   int C, block_n, n_tiles_n, bwd;
   int x_is_act;               // backward: `x` holds the saved activation act = x*s (the fused forward does not store x)
+  int abufs;                  // A-operand buffers: 2, or 1 when only that lets the whole channel range fit (C = 256)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
   const uint32_t a_base0 = base + kchunks * b_chunk_bytes;
   const int a_buf_bytes = kchunks * a_chunk_bytes;
   uint8_t* a_ptr0 = smem + kchunks * b_chunk_bytes;
-  uint8_t* tail = a_ptr0 + 2 * a_buf_bytes;
+  uint8_t* tail = a_ptr0 + P.abufs * a_buf_bytes;
   float* s_beta = reinterpret_cast<float*>(tail);                       // 256 floats (this CTA's n-tile)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256 * sizeof(float));
   const uint32_t bar_b = smem_u32(bars);          // gamma loaded
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
         mbar_wait(bar_a2 + 8 * buf, (it >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256;
-        const uint32_t a_addr = a_base0 + buf * a_buf_bytes;
+        const uint32_t a_addr = a_base0 + (P.abufs == 2 ? buf : 0) * a_buf_bytes;
         for (int kc = 0; kc < kchunks; ++kc) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
     const int cols_half = P.block_n / 2;
 
     auto stage1 = [&](long long tile, int buf) {
-      uint8_t* a_buf = a_ptr0 + buf * a_buf_bytes;
+      uint8_t* a_buf = a_ptr0 + (P.abufs == 2 ? buf : 0) * a_buf_bytes;
       const long long pix0 = tile * 128;
       for (int v0 = wt; v0 < vecs; v0 += kIgdnWorkers * 4) {
         uint4 xv[4], gv[4], sv[4];
@@ -237,9 +238,12 @@ __global__ void __launch_bounds__(kIgdnThreads, 1) k_igdn_tc(const __grid_consta
     for (; tile < num_tiles; tile += group_ctas, ++it) {
       const int buf = it & 1;
       const long long next = tile + group_ctas;
-      if (next < num_tiles) stage1(next, buf ^ 1);
+      if (P.abufs == 2 && next < num_tiles) stage1(next, buf ^ 1);
       mbar_wait(bar_acc + 8 * buf, (it >> 1) & 1);
       tcgen05_fence_after();
+      // one A buffer: the MMAs of this tile have finished reading it (bar_acc), so the next tile's operand is built now and
+      // its MMAs run while stage 3 drains this tile's accumulator (the accumulators stay double-buffered)
+      if (P.abufs == 1 && next < num_tiles) stage1(next, buf ^ 1);
       stage3(tile, buf);
     }
   }
@@ -265,15 +269,19 @@ int igdn_tc_create(const __nv_bfloat16* gamma_op, int C, long long pixels, int b
   IgdnParams& P = c->P;
   P.C = C; P.pixels = pixels; P.bwd = bwd;
   // largest channel tile (multiple of 64, <= 256, dividing C) whose operands fit in shared memory
-  int bn = 0;
-  for (int cand = 256; cand >= 64; cand -= 64) {
+  // Prefer covering all channels in one tile (every pixel tile is then read and its A operand built once), with a single
+  // A buffer if that is what it takes (C = 256: 128 KB of gamma + 64 KB of operand); narrower tiles only as a last resort.
+  int bn = 0, abufs = 2;
+  for (int cand = 256; cand >= 64 && bn == 0; cand -= 64) {
     if (C % cand) continue;
-    const long long need = 1024LL + (C / 64) * (cand * 128LL) + 2LL * (C / 64) * 16384 + 1024 + 256;
-    if (need <= 227 * 1024) { bn = cand; break; }
+    for (int ab = 2; ab >= 1; --ab) {
+      const long long need = 1024LL + (C / 64) * (cand * 128LL) + static_cast<long long>(ab) * (C / 64) * 16384 + 1024 + 256;
+      if (need <= 227 * 1024) { bn = cand; abufs = ab; break; }
+    }
   }
   SGA_CHECK(bn > 0, "IGDN operands do not fit in shared memory for C=%d", C);
-  P.block_n = bn; P.n_tiles_n = C / bn;
-  c->smem_bytes = 1024 + (C / 64) * (bn * 128) + 2 * (C / 64) * 16384 + 1024 + 256;
+  P.block_n = bn; P.n_tiles_n = C / bn; P.abufs = abufs;
+  c->smem_bytes = 1024 + (C / 64) * (bn * 128) + abufs * (C / 64) * 16384 + 1024 + 256;
   const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C)};
   const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
   const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};

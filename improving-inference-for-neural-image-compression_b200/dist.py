@@ -11,7 +11,13 @@ EVAL_BATCH_NUM_PIXELS = 1e7   # configs.py:5
 
 
 def eval_batch_size(num_pixels_per_image):
-    return int(round(EVAL_BATCH_NUM_PIXELS / num_pixels_per_image))   # configs.py:8-9
+    """configs.get_eval_batch_size (configs.py:8-9).  The pixel budget is sga_b200.configs.eval_batch_num_pixels; the
+    environment variable SGA_EVAL_BATCH_NUM_PIXELS overrides it (tests use it to get several reference batches out of
+    small images)."""
+    import os
+    from . import configs
+    budget = float(os.environ.get("SGA_EVAL_BATCH_NUM_PIXELS", configs.eval_batch_num_pixels))
+    return int(round(budget / num_pixels_per_image))
 
 
 def reference_batches(num_images, num_pixels_per_image):

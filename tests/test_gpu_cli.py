@@ -88,3 +88,43 @@ def test_compress_cli_bits_back(tmp_path):
     assert all(d[k].shape == (2,) for k in d.files)
     assert np.allclose(d["est_bpp"], d["est_y_bpp"] + d["est_z_bpp"] - d["est_bpp_back"], rtol=1e-4, atol=1e-5)
     assert np.isfinite(d["psnr"]).all()
+
+
+def test_compress_cli_many_reference_batches_opt_record_and_reconstruction(tmp_path):
+    """An input that spans several reference batches (configs.py:5-9; forced here with a small pixel budget): one engine per
+    batch, all advancing together, the reference's per-batch log blocks in batch order, per-image results in input order and
+    equal to what each batch gives when compressed on its own (n_ref and the noise key are per batch).  Also the optional
+    outputs: opt-*.npz (sga.py:271-278) and, for a single image, recon-*.png (sga.py:280-291)."""
+    rn, inp = _setup(tmp_path, n=5, h=64, w=64)
+    env = dict(os.environ, SGA_EVAL_BATCH_NUM_PIXELS=str(2 * 64 * 64))      # batches of 2, 2, 1 images
+    base = [sys.executable, os.path.join(ROOT, "sga.py"), "--num_filters", "64", "--checkpoint_dir", str(tmp_path / "ckpt"),
+            "compress", "--sga_its", "25", "--operand", "f32", "--save_opt_record"]
+    r = subprocess.run(base + ["--results_dir", str(tmp_path / "res"), rn, str(inp)], capture_output=True, text=True,
+                       timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("----RD Optimization----") == 3 and "SGA loop: 25 iterations of 5 images (3 reference batches)" in r.stdout
+    assert r.stdout.count("it=10, T=0.500") == 3                       # log_itv = 10 with the optimisation record on
+    full = np.load(tmp_path / "res" / ("rd-sga-lmbda=0.01+%s-input=imgs.npy.npz" % rn))
+    rec = np.load(tmp_path / "res" / ("opt-sga-lmbda=0.01+%s-input=imgs.npy.npz" % rn))
+    assert list(rec["its"]) == [0, 10, 20, 24] and rec["rd_loss"].shape == (4,) and np.isfinite(rec["rd_loss"]).all()
+    # the last batch (image 4 alone, n_ref = 1, noise key 2) compressed on its own must differ only by the noise key:
+    # compress images 0-1 alone (batch 0: same key 0, same n_ref 2) and compare exactly
+    X = np.load(inp)
+    np.save(tmp_path / "first.npy", X[:2])
+    (tmp_path / "res1").mkdir()
+    r1 = subprocess.run(base + ["--results_dir", str(tmp_path / "res1"), rn, str(tmp_path / "first.npy")], capture_output=True,
+                        text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    first = np.load(tmp_path / "res1" / ("rd-sga-lmbda=0.01+%s-input=first.npy.npz" % rn))
+    for k in ("psnr", "est_bpp", "mse"):
+        assert np.allclose(full[k][:2], first[k], rtol=1e-5, atol=1e-6), k
+    # single image: reconstruction PNG
+    from PIL import Image
+    Image.fromarray(X[0]).save(tmp_path / "one.png")
+    (tmp_path / "res2").mkdir()
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "sga.py"), "--num_filters", "64", "--checkpoint_dir", str(tmp_path / "ckpt"),
+                         "compress", "--sga_its", "6", "--save_reconstruction", "--results_dir", str(tmp_path / "res2"), rn,
+                         str(tmp_path / "one.png")], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    png = tmp_path / "res2" / ("recon-sga-lmbda=0.01-rd_opt_its=6+%s-input=one.png.png" % rn)
+    assert png.exists() and np.asarray(Image.open(png)).shape == (64, 64, 3)
