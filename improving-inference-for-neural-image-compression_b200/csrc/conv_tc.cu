@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
   // FUSE == 1 (two-pass forward fusion) is only instantiated for NF = 256, where the split-warp kernel of
   // conv_igdn_fwd_tc.cu does not fit in TMEM (2 x 256 accumulator columns leave no room for the mixing result)
-  static_assert(FUSE != 1 || NF == 256, "the forward fusion of NF <= 192 lives in conv_igdn_fwd_tc.cu");
+  static_assert(FUSE != 1 || NF == 256 || NF == 192, "the forward fusion of NF <= 128 lives in conv_igdn_fwd_tc.cu");
   // accumulator buffers: two (the epilogue of tile i overlaps the MMAs of tile i+1) unless 2*NF + NF/2 > 512 TMEM
   // columns -- NF = 256: one accumulator + the N/2-column mixing result = 384 columns; the accumulator is released after
   // pass 1 (its content lives on in registers as packed bf16), so the tensor pipe only idles during pass 1
@@ -530,7 +530,7 @@ typedef void (*TcKernel)(const TcParams);
 template <int CG>
 static TcKernel select_kernel_cg(int fuse, int nf) {
   if (fuse == 0) return k_conv_tc<0, 64, kPlainGroups, CG>;
-  if (fuse == 1) return k_conv_tc<1, 256, 4, CG>;          // two-pass forward fusion: NF = 256 only
+  if (fuse == 1) return nf == 256 ? k_conv_tc<1, 256, 4, CG> : k_conv_tc<1, 192, 3, CG>;   // two-pass forward fusion
   if (nf == 256) return k_conv_tc<2, 256, 4, CG>;
   return nf == 192 ? k_conv_tc<2, 192, 3, CG> : (nf == 128 ? k_conv_tc<2, 128, 2, CG> : k_conv_tc<2, 64, 1, CG>);
 }
@@ -568,7 +568,11 @@ static int launch_tc(const TcConv* c, const TcParams& P, cudaStream_t st) {
 
 bool tc_conv_can_fuse(int cout) { return cout == 64 || cout == 128 || cout == 192 || cout == 256; }
 // NF = 256 does not fit the split-warp forward kernel (TMEM): its forward fusion is the two-pass epilogue of k_conv_tc
-static bool fwd_two_pass(int cout) { return cout == 256; }
+// (SGA_FWD_TWO_PASS=1 selects it for NF = 192 as well: A/B switch against the split-warp kernel)
+static bool fwd_two_pass(int cout) {
+  static const bool force = getenv("SGA_FWD_TWO_PASS") != nullptr;
+  return cout == 256 || (force && cout == 192);
+}
 
 int tc_conv_create(const ConvPlan& plan, const __nv_bfloat16* x, const __nv_bfloat16* w_kmajor, int fuse,
                    const __nv_bfloat16* mix_op, TcConv** out) {
