@@ -80,6 +80,8 @@ struct sga_ctx {
   bf16 *b_zt, *b_h0, *b_h1, *b_yt, *b_gh2, *b_xpre[3], *b_s[3], *b_act[3], *b_gx4, *b_ga[3], *b_gb[3], *b_gh1, *b_gh0;
   TcConv *tc_hs[3] = {0, 0, 0}, *tc_gs[3] = {0, 0, 0}, *tc_hs_d[3] = {0, 0, 0}, *tc_gs_d[3] = {0, 0, 0};
   IgdnTc *ig_f[3] = {0, 0, 0}, *ig_b[3] = {0, 0, 0};
+  TcConv* tc_ig2 = nullptr;     // C = 256: IGDN_2 backward as the fused epilogue of an identity 1x1 "conv" over d loss / d act_2
+  bf16* ident_b = nullptr;
   L3Tc* l3 = nullptr;
   bool fused = false;   // IGDN runs inside the (de)conv epilogues (num_filters in {64,128,192})
   int split0 = 0;       // y_tilde / z_tilde enter g_s / h_s layer 0 as hi|lo bf16 pairs (K = 2C), see store_operand_pair
@@ -364,7 +366,7 @@ static int forward_backward_bf16(sga_ctx* c, const float* x, const float* y, con
         PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
       } else {
         PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
-        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_act[2], c->b_s[2], c->b_gb[2], st, 1));
+        PROF(c, SGA_PROF_IGDN_BWD, st, tc_conv_launch_igdn_bwd(c->tc_ig2, c->b_act[2], c->b_s[2], c->b_gb[2], st));
       }
       PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
       PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
@@ -465,9 +467,9 @@ static int step_bf16(sga_ctx* c, const float* x, const float* y, const float* z,
       // layer-3 dgrad, IGDN_1 / IGDN_0 inside the dgrad convs of layers 2 / 1
       if (l3_fusable(d.C)) {
         PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad_igdn(c->l3, c->b_gx4, c->b_gb[2], st));
-      } else {   // C = 256: x_2 = act_2 / s_2 inside the stand-alone IGDN backward
+      } else {   // C = 256: IGDN_2 backward as the fused epilogue of an identity 1x1 conv over d loss / d act_2
         PROF(c, SGA_PROF_L3_DGRAD, st, l3_tc_dgrad(c->l3, c->b_gx4, c->b_ga[2], st));
-        PROF(c, SGA_PROF_IGDN_BWD, st, igdn_tc_backward(c->ig_b[2], c->b_ga[2], c->b_act[2], c->b_s[2], c->b_gb[2], st, 1));
+        PROF(c, SGA_PROF_IGDN_BWD, st, tc_conv_launch_igdn_bwd(c->tc_ig2, c->b_act[2], c->b_s[2], c->b_gb[2], st));
       }
       PROF(c, SGA_PROF_CONV_GS + 5, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[2], c->b_act[1], c->b_s[1], c->b_gb[1], st));
       PROF(c, SGA_PROF_CONV_GS + 4, st, tc_conv_launch_igdn_bwd(c->tc_gs_d[1], c->b_act[0], c->b_s[0], c->b_gb[0], st));
@@ -634,6 +636,7 @@ int sga_destroy(sga_ctx* c) {
     igdn_tc_destroy(c->ig_f[i]); igdn_tc_destroy(c->ig_b[i]);
   }
   l3_tc_destroy(c->l3);
+  tc_conv_destroy(c->tc_ig2);
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->main) cudaStreamDestroy(c->main);
@@ -717,8 +720,23 @@ int sga_bind_weights(sga_ctx* c, const sga_weights* w, void* stream) {
         SGA_TRY(igdn_tc_create(c->gs_gamma_b[i], C, pix, 1, &c->ig_b[i]));
       }
     }
-    if (c->fused && !l3_fusable(C))
-      SGA_TRY(igdn_tc_create(c->gs_gamma_b[2], C, static_cast<long long>(d.N) * d.Hs[3] * d.Ws[3], 1, &c->ig_b[2]));
+    if (c->fused && !l3_fusable(C)) {
+      // The layer-3 dgrad cannot carry IGDN_2's backward at C = 256 (shared memory).  Rather than the stand-alone IGDN kernel
+      // (ALU-bound: 3.6 ms for the 604 M elements), run it as the fused backward epilogue of k_conv_tc over an identity
+      // 1x1 convolution of d loss / d act_2: the accumulator then holds g exactly, and the epilogue + mixing GEMM are the
+      // same tensor-rate code as in the other dgrads.
+      std::vector<float> eye(static_cast<size_t>(C) * C, 0.0f);
+      for (int i = 0; i < C; ++i) eye[static_cast<size_t>(i) * C + i] = 1.0f;
+      float* eye_d = nullptr;
+      SGA_TRY(c->alloc(&eye_d, static_cast<long long>(C) * C));
+      SGA_TRY(c->alloc(&c->ident_b, static_cast<long long>(C) * C));
+      SGA_CUDA(cudaMemcpyAsync(eye_d, eye.data(), eye.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+      SGA_TRY(launch_f32_to_bf16(eye_d, static_cast<long long>(C) * C, c->ident_b, st));
+      SGA_CUDA(cudaStreamSynchronize(st));
+      ConvPlan plan;
+      SGA_TRY(make_conv_plan(kS1Corr, 1, 1, d.N, d.Hs[3], d.Ws[3], C, C, &plan));
+      SGA_TRY(tc_conv_create(plan, c->b_ga[2], c->ident_b, 2, c->gs_gamma_b[2], &c->tc_ig2));
+    }
     SGA_TRY(c->alloc(&c->l3_wscatter, 80 * C)); SGA_TRY(c->alloc(&c->l3_wgather, 80 * C));
     SGA_TRY(l3_pack_weights(c->gs[3].w, C, c->l3_wscatter, c->l3_wgather, st));
     // fused: the IGDN backward recovers x_2 from the saved act_2 and s_2 (the fused forward does not store x)
