@@ -10,17 +10,30 @@ import subprocess
 import sys
 
 
-def raw(rep):
+TIME_MS = {"s": 1e3, "second": 1e3, "ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6}
+BYTES_GB = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
+
+
+def raw(rep, with_units=False):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    if with_units:
+        return rows[0], rows[1], rows[2:]
     return rows[0], rows[2:]
 
 
 def table(rep):
-    hdr, data = raw(rep)
+    hdr, units, data = raw(rep, with_units=True)
     col = {h: i for i, h in enumerate(hdr)}
     def g(r, k):
-        return r[col[k]] if k in col else "-"
+        if k not in col:
+            return "-"
+        v, u = r[col[k]], units[col[k]]
+        if k == "gpu__time_duration.sum":
+            return float(v) * TIME_MS.get(u, 1.0)          # -> ms
+        if k.startswith("dram__bytes"):
+            return float(v) * BYTES_GB.get(u, 1.0)         # -> GB
+        return v
     print("| # | kernel | ms | tensor pipe % | DRAM rd GB | DRAM wr GB | DRAM % | L2 hit % | regs | top stalls |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     for n, r in enumerate(data):
