@@ -157,11 +157,17 @@ def test_gather_results_gloo_world2(tmp_path):
     script.write_text(
         "import os, sys, numpy as np, torch, torch.distributed as dist\n"
         "sys.path.insert(0, %r)\n"
-        "from sga_b200.dist import gather_rows, shard_range, allreduce_scalars\n"
+        "from sga_b200.dist import gather_rows, shard_range, allreduce_scalars, allgather_floats, rank_segments\n"
         "dist.init_process_group('gloo')\n"
         "r, ws = dist.get_rank(), dist.get_world_size()\n"
         "n = 5\n"
         "lo, hi = shard_range(n, r, ws)\n"
+        "segs = rank_segments(n, 1200 * 1200 * 4, r, ws)           # batches of 2 images: 2 + 2 + 1\n"
+        "assert sum(s['hi'] - s['lo'] for s in segs) == hi - lo and segs[0]['lo'] == lo\n"
+        "per_batch = [0.0, 0.0, 0.0]\n"
+        "for s in segs: per_batch[s['batch']] += s['hi'] - s['lo']\n"
+        "assert allreduce_scalars(per_batch, device='cpu') == [2.0, 2.0, 1.0]   # the per-batch log reduction of cli.compress\n"
+        "assert allgather_floats(float(r + 1)) == [1.0, 2.0]\n"
         "rows = np.stack([np.arange(lo, hi) * 10.0 + k for k in range(5)], axis=1).astype(np.float32)\n"
         "full = gather_rows(rows, n, r, ws, device='cpu')\n"
         "tot = allreduce_scalars([float(hi - lo), 1.0], device='cpu')\n"
