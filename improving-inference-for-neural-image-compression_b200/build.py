@@ -1,6 +1,7 @@
 """Builds libsga_b200.so in-tree with nvcc for sm_100a (no torch dependency in the library).
 
-    python improving-inference-for-neural-image-compression_b200/build.py [--force] [--verbose]
+    python improving-inference-for-neural-image-compression_b200/build.py [--force] [--verbose] [--dbg]
+(--dbg: -DSGA_DBG, compiles the in-kernel wait-cycle accounting of the (de)conv kernels in; env SGA_DBG=8 then prints it)
 """
 import os
 import subprocess
@@ -29,7 +30,7 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, dbg=False):
     if not force and not _stale():
         return LIB
     objdir = os.path.join(HERE, "build")
@@ -38,7 +39,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DSGA_DBG"] if dbg else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
@@ -54,4 +56,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv or "--dbg" in sys.argv, verbose="--verbose" in sys.argv, dbg="--dbg" in sys.argv))

@@ -107,7 +107,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_conv_igdn_fwd(const __grid_c
   auto arrive_lead = [](uint32_t local_bar, uint32_t lead_bar) {
     if (CG == 2) mbar_arrive_cluster(lead_bar); else mbar_arrive(local_bar);
   };
+  // wait-cycle accounting (clock64 / printf) is a development aid: compiled in only with -DSGA_DBG (build.py --dbg),
+  // otherwise dbg_t is a compile-time false and every instrumented statement reduces to the statement itself
+#ifdef SGA_DBG
   const bool dbg_t = (P.dbg & 8) != 0;
+#else
+  constexpr bool dbg_t = false;
+#endif
   long long dbg_w[4] = {0, 0, 0, 0};
   const long long dbg_t0 = dbg_t ? clock64() : 0;
   const bool dbg_print = dbg_t && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 74);

@@ -174,7 +174,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) k_conv_tc(const __grid_consta
   auto wait_x = [](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
   auto arrive_lead = [](uint32_t local_bar, uint32_t lead_bar) { if (CG == 2) mbar_arrive_cluster(lead_bar); else mbar_arrive(local_bar); };
   // SGA_DBG & 8: per-role wait-cycle accounting, printed by the first and one middle CTA (development aid)
+  // wait-cycle accounting (clock64 / printf) is a development aid: compiled in only with -DSGA_DBG (build.py --dbg),
+  // otherwise dbg_t is a compile-time false and every instrumented statement reduces to the statement itself
+#ifdef SGA_DBG
   const bool dbg_t = (P.dbg & 8) != 0;
+#else
+  constexpr bool dbg_t = false;
+#endif
   long long dbg_w[4] = {0, 0, 0, 0};
   const long long dbg_t0 = dbg_t ? clock64() : 0;
   unsigned long long dbg_g0 = 0;

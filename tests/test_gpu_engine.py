@@ -356,3 +356,19 @@ def test_bf16_loop_against_fp32_loop_north_star_tolerance():
     assert (d_bpp <= np.maximum(1e-3, 2.0 * band.max())).all(), (d_bpp, band)
     ctrl_bias = max(abs((c[0] - bpp_f).mean()) for c in ctrl)
     assert abs((bpp_b - bpp_f).mean()) <= max(1e-3 * bpp_f.mean(), 2.0 * ctrl_bias), ((bpp_b - bpp_f).mean(), ctrl_bias)
+
+
+@pytest.mark.parametrize("C,n,h,w", [(64, 1, 96, 80), (256, 1, 128, 128)])
+def test_grad_bf16_unfused_fallback(C, n, h, w, monkeypatch):
+    """SGA_NO_FUSE=1: plain (de)conv kernels + the stand-alone tensor-core IGDN kernel (k_igdn_tc) forward and backward --
+    the path for any num_filters the fused epilogues do not cover -- against the oracle, same tolerances as the fused path."""
+    monkeypatch.setenv("SGA_NO_FUSE", "1")
+    W, Wt, x, y, z = make_case(C, n, h, w, seed=C + 3)
+    ref = O.sga_graph(x, y, z, Wt, 0.35, O.draw_noise(y, z, 3, 11), 0.01)
+    eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=3)
+    gy, gz, stats = eng.grad(x.cuda(), y.cuda(), z.cuda(), 0.35, 11)
+    s = eng.unpack_stats(stats.cpu().numpy())
+    assert abs(s["train_bpp"] - float(ref["train_bpp"])) <= 5e-4 * abs(float(ref["train_bpp"]))
+    assert abs(s["train_mse"] - float(ref["train_mse"])) <= 1.5e-3 * abs(float(ref["train_mse"]))
+    assert rms_rel_err(gy, ref["grad_y"]) < 1e-2 and rms_rel_err(gz, ref["grad_z"]) < 9e-2
+    eng.close()
