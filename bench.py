@@ -399,7 +399,7 @@ def main_ours(args, rank, ws, local, wl):
         for k, v in layer3_bytes(j["n"], H, Wd, C).items():
             l3b[k] += v
     fused = C in (64, 128, 192, 256)
-    l3_fused = C in (64, 128, 192)         # C = 256: the layer-3 dgrad and the IGDN_2 backward are separate launches
+    l3_fused = C in (64, 128, 192, 256) and not (C == 256 and os.environ.get("SGA_L3_NO_FUSE256"))
     conv_labels = {"hs0_fwd": "hs0", "hs1_fwd": "hs1", "hs2_fwd": "hs2", "hs0_dgrad": "hs0", "hs1_dgrad": "hs1",
                    "hs2_dgrad": "hs2", "gs0_fwd": "gs0", "gs1_fwd": "gs1", "gs2_fwd": "gs2", "gs0_dgrad": "gs0",
                    "gs1_dgrad": "gs1", "gs2_dgrad": "gs2"}

@@ -164,9 +164,12 @@ static void compute_dims(const sga_config& c, Dims& d) {
   d.nz = static_cast<long long>(d.N) * d.Hz * d.Wz * d.C;
 }
 
-// the layer-3 dgrad can carry the IGDN_2 backward in its epilogue only while gamma (C x C) and a saved x / s tile pair fit
-// in shared memory beside the gather operands: C <= 192 (layer3_tc.cu)
-static bool l3_fusable(int C) { return C == 64 || C == 128 || C == 192; }
+// the layer-3 dgrad carries the IGDN_2 backward in its epilogue: with gamma, a saved x / s tile pair and the gather operands
+// in shared memory for C <= 192, and in "direct" mode (x / s from global memory, one shared weights / t buffer) for C = 256
+static bool l3_fusable(int C) {
+  if (C == 256) return getenv("SGA_L3_NO_FUSE256") == nullptr;   // the direct-mode kernel; the switch keeps the fallback testable
+  return C == 64 || C == 128 || C == 192;
+}
 
 static long long gs_elems(const Dims& d, int level) {  // level 1..3: output of g_s layer level-1
   return static_cast<long long>(d.N) * d.Hs[level] * d.Ws[level] * d.C;
@@ -613,8 +616,12 @@ int sga_create(const sga_config* cfg, sga_ctx** out) {
     }
   }
   if (st == SGA_OK && bf) {
-    cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
+    // The library's own main stream gets the highest priority and the side stream the lowest: with SGA_PRIO=1 sga_loop runs
+    // the synthesis chain on it, so that the hyper path's blocks only fill what the synthesis kernels leave free.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->main, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -880,7 +887,9 @@ int sga_loop(sga_ctx* c, const float* x, float* y, float* z, float* m_y, float* 
   // 0.566 vs 0.562 ms.
   const char* eg = getenv("SGA_GRAPH");
   const bool graphed = c->cfg.operand == SGA_OPERAND_BF16 && !c->prof && eg != nullptr && eg[0] == '1';
-  if (graphed && (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)) {
+  const char* ep = getenv("SGA_PRIO");
+  const bool own_main = (ep != nullptr && ep[0] == '1' && st != c->main && !c->prof && c->cfg.operand == SGA_OPERAND_BF16);
+  if (own_main || (graphed && (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread))) {
     // the default streams cannot be captured: run on the context's own stream, ordered after / before the caller's
     SGA_CUDA(cudaEventRecord(c->ev_in, st));
     SGA_CUDA(cudaStreamWaitEvent(c->main, c->ev_in, 0));

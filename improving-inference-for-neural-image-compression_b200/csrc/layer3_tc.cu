@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(kL3dThreads, 1) k_l3_dgrad(const __grid_consta
 struct alignas(64) L3DgradFusedParams {
   CUtensorMap gmap;            // gamma [n = C rows][k = C cols] bf16, box {64, C}
   CUtensorMap xmap, smap;      // saved act_2 (= x_2*s_2) / s_2 [N,Hin,Win,C] bf16, box {64, 16, 8, 1}
+  const __nv_bfloat16* x_ptr;  // the same tensors as plain pointers (NF = 256: read straight from global memory)
+  const __nv_bfloat16* s_ptr;
   const __nv_bfloat16* gx;     // [N,Ho,Wo,4]
   const __nv_bfloat16* wpack;  // [10][C][8]
   __nv_bfloat16* out;          // d loss / d x_2
@@ -488,9 +490,14 @@ __device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, i
   }
 }
 
+// NF = 256 ("direct" mode): gamma alone is 128 KB, so there is no room for x / s tiles and resident gather weights.  The
+// workers read their act / s chunks straight from global memory (64-byte row segments, prefetched before the accumulator
+// is awaited), and ONE 64 KB buffer holds the gather weights (40 KB) while the gather GEMM runs and the mixing operand t
+// afterwards; warp 1 re-loads the weights (one 1-D bulk copy from L2) as soon as the mixing GEMM has read t.
 template <int NF>
 __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
   pdl_launch_dependents();
+  constexpr bool kDirect = (NF == 256);
   constexpr int G = NF / 64;                 // worker groups (column split)
   constexpr int kWorkers = 128 * G;
   constexpr int kKc = NF / 64;               // K chunks of the mixing GEMM
@@ -510,10 +517,11 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   uint8_t* a2_ptr = smem + kGammaBytes;
   const uint32_t s_base = a2_base + kTileBytes;
   uint8_t* s_ptr = a2_ptr + kTileBytes;
-  const uint32_t b_base = s_base + kTileBytes;
-  uint8_t* b_ptr = s_ptr + kTileBytes;
-  const uint32_t a_base = b_base + kBPad;
-  uint8_t* a_ptr = b_ptr + kBPad;
+  // direct mode: no s tile; the gather weights share the x / t buffer
+  const uint32_t b_base = kDirect ? a2_base : s_base + kTileBytes;
+  uint8_t* b_ptr = kDirect ? a2_ptr : s_ptr + kTileBytes;
+  const uint32_t a_base = kDirect ? a2_base + kTileBytes : b_base + kBPad;
+  uint8_t* a_ptr = kDirect ? a2_ptr + kTileBytes : b_ptr + kBPad;
   uint8_t* reg_ptr = a_ptr + kAIm;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reg_ptr + kRegBytes);
   const uint32_t bar_g = smem_u32(bars);             // gamma loaded (tx)
@@ -528,14 +536,18 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kBBytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(b_ptr)[i] = __ldg(reinterpret_cast<const uint4*>(P.wpack) + i);
-  fence_proxy_async_smem();
+  if (!kDirect) {
+    for (int i = threadIdx.x; i < kBBytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(b_ptr)[i] = __ldg(reinterpret_cast<const uint4*>(P.wpack) + i);
+    fence_proxy_async_smem();
+  }
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&P.gmap);
-      tma_prefetch_desc(&P.xmap);
-      tma_prefetch_desc(&P.smap);
+      if (!kDirect) {
+        tma_prefetch_desc(&P.xmap);
+        tma_prefetch_desc(&P.smap);
+      }
       mbar_init(bar_g, 1);
       mbar_init(bar_afull, kWorkers);
       mbar_init(bar_aempty, 1);
@@ -588,6 +600,7 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
       mbar_wait(bar_afull, it & 1);
+      if (kDirect) mbar_wait(bar_xfull, it & 1);    // the gather weights are back in the shared x / t buffer
       tcgen05_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -602,6 +615,17 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
   } else if (warp == 1) {
     // ===================== TMA producer: saved x and s tiles (warp-uniform loop) =====================
     int it = 0;
+    if (kDirect) {
+      // the only thing to stream is the gather-weight block: before tile 0, then after every mixing GEMM (which reads t
+      // out of the same buffer)
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        if (it > 0) mbar_wait(bar_nfull, (it - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_xfull, kBBytes);
+          bulk_load_1d(b_base, P.wpack, kBBytes, bar_xfull);
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
       const int h0 = (tt / P.tiles_w) * 8, w0 = (tt % P.tiles_w) * 16;
@@ -670,6 +694,11 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       } else if (G == 2) {
         if (bpart == 0) l3_build_groups<0, 5>(reg, tr, tcx, a_ptr, brow);
         else l3_build_groups<5, 5>(reg, tr, tcx, a_ptr, brow);
+      } else if (G == 4) {
+        if (bpart == 0) l3_build_groups<0, 3>(reg, tr, tcx, a_ptr, brow);
+        else if (bpart == 1) l3_build_groups<3, 3>(reg, tr, tcx, a_ptr, brow);
+        else if (bpart == 2) l3_build_groups<6, 2>(reg, tr, tcx, a_ptr, brow);
+        else l3_build_groups<8, 2>(reg, tr, tcx, a_ptr, brow);
       } else {
         l3_build_groups<0, 10>(reg, tr, tcx, a_ptr, brow);
       }
@@ -692,8 +721,26 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * NF;
       // ---- pass 1: g (TMEM), x and s (smem)  ->  t in place of x, g*s and x kept as packed bf16
       uint32_t keep[2][16], xk[2][16];
-      mbar_wait(bar_sfull, it & 1);
-      mbar_wait(bar_xfull, it & 1);
+      uint32_t sg[kDirect ? 2 : 1][16];
+      if (kDirect) {
+        // act / s chunks of this thread's pixel row straight from global memory, in flight while the accumulator is awaited
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = grp + h * G;
+          if (valid) {
+            ld_global_nc_v8(P.x_ptr + off0 + c * 32, &xk[h][0]);
+            ld_global_nc_v8(P.x_ptr + off0 + c * 32 + 16, &xk[h][8]);
+            ld_global_nc_v8(P.s_ptr + off0 + c * 32, &sg[kDirect ? h : 0][0]);
+            ld_global_nc_v8(P.s_ptr + off0 + c * 32 + 16, &sg[kDirect ? h : 0][8]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { xk[h][e] = 0u; sg[kDirect ? h : 0][e] = 0x3F803F80u; }
+          }
+        }
+      } else {
+        mbar_wait(bar_sfull, it & 1);
+        mbar_wait(bar_xfull, it & 1);
+      }
       mbar_wait(bar_tfull, it & 1);
       tcgen05_fence_after();
 #pragma unroll
@@ -704,13 +751,18 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
         uint8_t* xc = a2_ptr + (c >> 1) * 16384;
         const uint8_t* sc = s_ptr + (c >> 1) * 16384;
         uint32_t sv[16];
+        if (kDirect) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t o = sw128_offset(row, (c & 1) * 4 + u);
-          const uint4 xq = *reinterpret_cast<const uint4*>(xc + o);
-          const uint4 sq = *reinterpret_cast<const uint4*>(sc + o);
-          xk[h][4 * u] = xq.x; xk[h][4 * u + 1] = xq.y; xk[h][4 * u + 2] = xq.z; xk[h][4 * u + 3] = xq.w;
-          sv[4 * u] = sq.x; sv[4 * u + 1] = sq.y; sv[4 * u + 2] = sq.z; sv[4 * u + 3] = sq.w;
+          for (int e = 0; e < 16; ++e) sv[e] = sg[kDirect ? h : 0][e];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t o = sw128_offset(row, (c & 1) * 4 + u);
+            const uint4 xq = *reinterpret_cast<const uint4*>(xc + o);
+            const uint4 sq = *reinterpret_cast<const uint4*>(sc + o);
+            xk[h][4 * u] = xq.x; xk[h][4 * u + 1] = xq.y; xk[h][4 * u + 2] = xq.z; xk[h][4 * u + 3] = xq.w;
+            sv[4 * u] = sq.x; sv[4 * u + 1] = sq.y; sv[4 * u + 2] = sq.z; sv[4 * u + 3] = sq.w;
+          }
         }
         tmem_ld_wait();
 #pragma unroll
@@ -881,7 +933,9 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     DF.N = N; DF.Hin = Hin; DF.Win = Win; DF.C = C; DF.wpack = w_gather;
     DF.tiles_h = D.tiles_h; DF.tiles_w = D.tiles_w; DF.total_tiles = D.total_tiles;
     { const char* e = getenv("SGA_L3_PREFETCH"); DF.prefetch = e ? (atoi(e) > 0 ? 1 : 0) : 0; }
-    c->fused_ok = (C == 64 || C == 128 || C == 192) && gamma_bwd_op != nullptr && x_saved != nullptr && s_saved != nullptr;
+    c->fused_ok = (C == 64 || C == 128 || C == 192 || C == 256) && gamma_bwd_op != nullptr && x_saved != nullptr &&
+                  s_saved != nullptr;
+    DF.x_ptr = x_saved; DF.s_ptr = s_saved;
     if (c->fused_ok) {
       const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                                 static_cast<uint64_t>(N)};
@@ -903,6 +957,8 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     }
     const int kc = C / 64;
     c->df_smem = 1024 + kc * C * 128 + 2 * kc * 16384 + ((b_bytes + 1023) / 1024) * 1024 + 20480 + reg_bytes + 256;
+    if (C == 256)       // direct mode: gamma | shared weights / t buffer | im2col | patch
+      c->df_smem = 1024 + kc * C * 128 + kc * 16384 + 20480 + reg_bytes + 256;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -911,6 +967,7 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   *out = c;
@@ -941,13 +998,14 @@ int l3_tc_dgrad(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cuda
 bool l3_tc_can_fuse_igdn(const L3Tc* c) { return c->fused_ok; }
 
 int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out, cudaStream_t st) {
-  SGA_CHECK(c->fused_ok, "layer-3 dgrad + IGDN backward fusion needs C in {64,128,192} and the gamma operand at create");
+  SGA_CHECK(c->fused_ok, "layer-3 dgrad + IGDN backward fusion needs C in {64,128,192,256} and the gamma operand at create");
   if (c->DF.total_tiles == 0) return SGA_OK;
   const int C = c->DF.C;
   L3DgradFusedParams D = c->DF;
   D.gx = gx; D.out = out;
   const int threads = 64 + 128 * (C / 64);
-  if (C == 192) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
+  if (C == 256) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<256>, c->d_grid, threads, c->df_smem, st, D));
+  else if (C == 192) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
   else if (C == 128) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<128>, c->d_grid, threads, c->df_smem, st, D));
   else SGA_TRY(launch_pdl(k_l3_dgrad_igdn<64>, c->d_grid, threads, c->df_smem, st, D));
   return SGA_OK;
