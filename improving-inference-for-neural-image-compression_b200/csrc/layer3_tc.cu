@@ -494,11 +494,18 @@ __device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, i
 // workers read their act / s chunks straight from global memory (64-byte row segments, prefetched before the accumulator
 // is awaited), and ONE 64 KB buffer holds the gather weights (40 KB) while the gather GEMM runs and the mixing operand t
 // afterwards; warp 1 re-loads the weights (one 1-D bulk copy from L2) as soon as the mixing GEMM has read t.
+// In direct mode the two point-wise passes are STATELESS: pass 1 only writes the mixing operand, pass 2 re-reads the
+// accumulator g (which therefore stays alive until pass 2 is done: the next tile's gather GEMM waits for it) and re-loads
+// act / s (L2 hits).  Keeping g*s and x as packed registers across the mixing GEMM, as the NF <= 192 variant does, needs
+// 32 registers per 32-column chunk on top of the working set: with 256 columns that spilled at every thread count tried
+// (576 threads / 96 registers: 2.0 ms, 68 % of the stall samples on local-memory loads).
+constexpr int l3_groups(int nf) { return nf / 64; }
 template <int NF>
-__global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
+__global__ void __launch_bounds__(64 + 128 * l3_groups(NF), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
   pdl_launch_dependents();
   constexpr bool kDirect = (NF == 256);
-  constexpr int G = NF / 64;                 // worker groups (column split)
+  constexpr int G = l3_groups(NF);           // worker groups (column split)
+  constexpr int NH = NF / (32 * G);          // 32-column chunks per worker warp: chunk c = grp + h * G, h < NH
   constexpr int kWorkers = 128 * G;
   constexpr int kKc = NF / 64;               // K chunks of the mixing GEMM
   constexpr int kGammaBytes = kKc * NF * 128;
@@ -600,7 +607,10 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       if (it > 0) mix(it - 1);                      // also guarantees the accumulator of tile it-1 is drained
       mbar_wait(bar_afull, it & 1);
-      if (kDirect) mbar_wait(bar_xfull, it & 1);    // the gather weights are back in the shared x / t buffer
+      if (kDirect) {
+        mbar_wait(bar_xfull, it & 1);               // the gather weights are back in the shared x / t buffer
+        if (it > 0) mbar_wait(bar_nempty, (it - 1) & 1);   // pass 2 of the previous tile has re-read its accumulator
+      }
       tcgen05_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -720,41 +730,63 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
       const bool valid = (i < P.Hin) && (j < P.Win);
       const long long off0 = ((static_cast<long long>(img) * P.Hin + i) * P.Win + j) * NF;
       // ---- pass 1: g (TMEM), x and s (smem)  ->  t in place of x, g*s and x kept as packed bf16
-      uint32_t keep[2][16], xk[2][16];
-      uint32_t sg[kDirect ? 2 : 1][16];
-      if (kDirect) {
-        // act / s chunks of this thread's pixel row straight from global memory, in flight while the accumulator is awaited
+      uint32_t keep[kDirect ? 1 : NH][16], xk[kDirect ? 1 : NH][16];
+      // direct mode works in units of 16 columns (half a chunk) with the operands of the next unit in flight: at 576 threads
+      // there are 96 registers per thread, and a whole 32-column chunk of accumulator + act + s + prefetch does not fit
+      uint32_t xg[8], sg[8];
+      auto load_xs = [&](int unit) {            // unit = 2 * h + half: this thread's pixel row, 16 columns of act and s
+        const int col = (grp + (unit >> 1) * G) * 32 + (unit & 1) * 16;
+        if (valid) {
+          ld_global_nc_v8(P.x_ptr + off0 + col, xg);
+          ld_global_nc_v8(P.s_ptr + off0 + col, sg);
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = grp + h * G;
-          if (valid) {
-            ld_global_nc_v8(P.x_ptr + off0 + c * 32, &xk[h][0]);
-            ld_global_nc_v8(P.x_ptr + off0 + c * 32 + 16, &xk[h][8]);
-            ld_global_nc_v8(P.s_ptr + off0 + c * 32, &sg[kDirect ? h : 0][0]);
-            ld_global_nc_v8(P.s_ptr + off0 + c * 32 + 16, &sg[kDirect ? h : 0][8]);
-          } else {
+          for (int e = 0; e < 8; ++e) { xg[e] = 0u; sg[e] = 0x3F803F80u; }
+        }
+      };
+      if constexpr (kDirect) {
+        load_xs(0);                             // in flight while the accumulator is awaited
+        mbar_wait(bar_tfull, it & 1);
+        tcgen05_fence_after();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { xk[h][e] = 0u; sg[kDirect ? h : 0][e] = 0x3F803F80u; }
+        for (int unit = 0; unit < 2 * NH; ++unit) {
+          const int c = grp + (unit >> 1) * G, half = unit & 1;
+          uint32_t r[16];
+          tmem_ld16(tmem_base + lane_off + c * 32 + half * 16, r);
+          uint32_t xa[8], sa[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { xa[e] = xg[e]; sa[e] = sg[e]; }
+          if (unit + 1 < 2 * NH) load_xs(unit + 1);
+          tmem_ld_wait();
+          uint8_t* xc = a2_ptr + (c >> 1) * 16384;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint32_t a2w[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int e = u * 4 + e4;
+              const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+              const float s0 = l3_bf16_lo(sa[e]), s1 = l3_bf16_hi(sa[e]);
+              const float r0 = l3_rcp(s0), r1 = l3_rcp(s1);
+              const float x0 = l3_bf16_lo(xa[e]) * r0, x1 = l3_bf16_hi(xa[e]) * r1;
+              a2w[e4] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
+            }
+            *reinterpret_cast<uint4*>(xc + sw128_offset(row, (c & 1) * 4 + half * 2 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
           }
         }
       } else {
         mbar_wait(bar_sfull, it & 1);
         mbar_wait(bar_xfull, it & 1);
-      }
-      mbar_wait(bar_tfull, it & 1);
-      tcgen05_fence_after();
+        mbar_wait(bar_tfull, it & 1);
+        tcgen05_fence_after();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = grp + h * G;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + c * 32, r);
-        uint8_t* xc = a2_ptr + (c >> 1) * 16384;
-        const uint8_t* sc = s_ptr + (c >> 1) * 16384;
-        uint32_t sv[16];
-        if (kDirect) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sv[e] = sg[kDirect ? h : 0][e];
-        } else {
+        for (int h = 0; h < NH; ++h) {
+          const int c = grp + h * G;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + c * 32, r);
+          uint8_t* xc = a2_ptr + (c >> 1) * 16384;
+          const uint8_t* sc = s_ptr + (c >> 1) * 16384;
+          uint32_t sv[16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const uint32_t o = sw128_offset(row, (c & 1) * 4 + u);
@@ -763,25 +795,25 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
             xk[h][4 * u] = xq.x; xk[h][4 * u + 1] = xq.y; xk[h][4 * u + 2] = xq.z; xk[h][4 * u + 3] = xq.w;
             sv[4 * u] = sq.x; sv[4 * u + 1] = sq.y; sv[4 * u + 2] = sq.z; sv[4 * u + 3] = sq.w;
           }
-        }
-        tmem_ld_wait();
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t a2w[4];
+          for (int u = 0; u < 4; ++u) {
+            uint32_t a2w[4];
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const int e = u * 4 + e4;
-            const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
-            const uint32_t aw = xk[h][e];                        // saved act = x*s: x = act / s
-            const uint32_t sw = valid ? sv[e] : 0x3F803F80u;     // out-of-image rows are zero-filled by TMA: s = 1
-            const float s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
-            const float r0 = l3_rcp(s0), r1 = l3_rcp(s1);
-            const float x0 = l3_bf16_lo(aw) * r0, x1 = l3_bf16_hi(aw) * r1;
-            xk[h][e] = pack_bf16(x0, x1);
-            keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
-            a2w[e4] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int e = u * 4 + e4;
+              const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+              const uint32_t aw = xk[h][e];                        // saved act = x*s: x = act / s
+              const uint32_t sw = valid ? sv[e] : 0x3F803F80u;     // out-of-image rows are zero-filled by TMA: s = 1
+              const float s0 = l3_bf16_lo(sw), s1 = l3_bf16_hi(sw);
+              const float r0 = l3_rcp(s0), r1 = l3_rcp(s1);
+              const float x0 = l3_bf16_lo(aw) * r0, x1 = l3_bf16_hi(aw) * r1;
+              xk[h][e] = pack_bf16(x0, x1);
+              keep[h][e] = pack_bf16(v0 * s0, v1 * s1);
+              a2w[e4] = pack_bf16(v0 * x0 * r0, v1 * x1 * r1);
+            }
+            *reinterpret_cast<uint4*>(xc + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
           }
-          *reinterpret_cast<uint4*>(xc + sw128_offset(row, (c & 1) * 4 + u)) = make_uint4(a2w[0], a2w[1], a2w[2], a2w[3]);
         }
       }
       fence_proxy_async_smem();
@@ -794,15 +826,50 @@ __global__ void __launch_bounds__(64 + 128 * (NF / 64), 1) k_l3_dgrad_igdn(const
         if (next + static_cast<int>(gridDim.x) < P.total_tiles) fetch_patch(next + gridDim.x);
       }
       // ---- pass 2
+      if constexpr (kDirect) {
+        // stateless: g from the accumulator (still alive: the next gather GEMM waits for bar_nempty), x = act / s again (L2)
+        load_xs(0);                             // in flight while the mixing GEMM finishes
+        mbar_wait(bar_nfull, it & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int unit = 0; unit < 2 * NH; ++unit) {
+          const int c = grp + (unit >> 1) * G, half = unit & 1;
+          uint32_t m[16], g[16];
+          tmem_ld16(tmem_base + kNormCol + lane_off + c * 32 + half * 16, m);
+          tmem_ld16(tmem_base + lane_off + c * 32 + half * 16, g);
+          uint32_t xa[8], sa[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { xa[e] = xg[e]; sa[e] = sg[e]; }
+          if (unit + 1 < 2 * NH) load_xs(unit + 1);
+          tmem_ld_wait();
+          if (unit == 2 * NH - 1) {             // accumulator and mixing result are in registers: release both
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_nempty);
+          }
+          if (valid) {
+            uint32_t o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float s0 = l3_bf16_lo(sa[e]), s1 = l3_bf16_hi(sa[e]);
+              const float x0 = l3_bf16_lo(xa[e]) * l3_rcp(s0), x1 = l3_bf16_hi(xa[e]) * l3_rcp(s1);
+              o[e] = pack_bf16(__uint_as_float(g[2 * e]) * s0 + x0 * __uint_as_float(m[2 * e]),
+                               __uint_as_float(g[2 * e + 1]) * s1 + x1 * __uint_as_float(m[2 * e + 1]));
+            }
+            st_global_v8(P.out + off0 + c * 32 + half * 16, o);
+          }
+        }
+        continue;
+      }
       mbar_wait(bar_nfull, it & 1);
       tcgen05_fence_after();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NH; ++h) {
         const int c = grp + h * G;
         uint32_t m[32];
         tmem_ld32(tmem_base + kNormCol + lane_off + c * 32, m);
         tmem_ld_wait();
-        if (h == 1) {                       // both chunks of the mixing result are in registers: release it
+        if (h == NH - 1) {                  // the last chunk of the mixing result is in registers: release it
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_nempty);
@@ -1003,7 +1070,7 @@ int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out,
   const int C = c->DF.C;
   L3DgradFusedParams D = c->DF;
   D.gx = gx; D.out = out;
-  const int threads = 64 + 128 * (C / 64);
+  const int threads = 64 + 128 * l3_groups(C);
   if (C == 256) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<256>, c->d_grid, threads, c->df_smem, st, D));
   else if (C == 192) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
   else if (C == 128) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<128>, c->d_grid, threads, c->df_smem, st, D));
