@@ -128,3 +128,35 @@ def test_compress_cli_many_reference_batches_opt_record_and_reconstruction(tmp_p
     assert r2.returncode == 0, r2.stdout + r2.stderr
     png = tmp_path / "res2" / ("recon-sga-lmbda=0.01-rd_opt_its=6+%s-input=one.png.png" % rn)
     assert png.exists() and np.asarray(Image.open(png)).shape == (64, 64, 3)
+
+
+def test_compress_cli_two_ranks_many_batches_match_one(tmp_path):
+    """Cross-batch sharding over 2 GPUs: 5 images in reference batches of 2, 2, 1 (forced by a small pixel budget), rank 0
+    holds images 0-2 (batch 0 and half of batch 1), rank 1 images 3-4 (the other half and batch 2).  Per-image results equal
+    the one-GPU run: n_ref, noise key and noise offset are those of the image's reference batch, not of the shard."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rn, inp = _setup(tmp_path, n=5, h=64, w=64)
+    env = dict(os.environ, SGA_EVAL_BATCH_NUM_PIXELS=str(2 * 64 * 64))
+    base = ["--num_filters", "64", "--checkpoint_dir", str(tmp_path / "ckpt"), "compress", "--sga_its", "12", "--operand", "f32"]
+    res = []
+    for tag, launcher in (("one", [sys.executable]),
+                          ("two", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29743"])):
+        rd = tmp_path / ("res_" + tag)
+        rd.mkdir()
+        r = subprocess.run(launcher + [os.path.join(ROOT, "sga.py")] + base + ["--results_dir", str(rd), rn, str(inp)],
+                           capture_output=True, text=True, timeout=900, cwd=str(tmp_path), env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("----RD Optimization----") == 3
+        res.append((np.load(rd / ("rd-sga-lmbda=0.01+%s-input=imgs.npy.npz" % rn)), r.stdout))
+    for k in ("psnr", "est_bpp", "est_y_bpp", "est_z_bpp", "mse"):
+        assert res[0][0][k].shape == (5,)
+        assert np.allclose(res[0][0][k], res[1][0][k], rtol=1e-5, atol=1e-6), (k, res[0][0][k], res[1][0][k])
+    # the per-batch log lines (batch-wide sums re-assembled over the ranks) agree too
+    import re
+    lines = [[l for l in out.splitlines() if l.startswith("it=11,")] for _, out in res]
+    assert len(lines[0]) == 3 and len(lines[1]) == 3, lines
+    nums = [np.array([[float(v) for v in re.findall(r"=(-?[0-9.]+)", l)] for l in ls]) for ls in lines]
+    assert np.allclose(nums[0], nums[1], rtol=2e-4, atol=2e-4), lines

@@ -116,6 +116,17 @@ def test_cli_surface_matches_reference():
     assert a.verbose and a.lmbda == 0.08 and a.sga_its == 10 and a.t0 == 350 and a.output_file == "o"
     with pytest.raises(SystemExit):
         parse_args(["sga.py"])
+    assert a.save_opt_record is False and a.save_reconstruction is False      # configs.save_opt_record / sga.py:34 as flags
+    a = parse_args(["sga.py", "--num_filters", "192", "compress", "--save_opt_record", "--save_reconstruction", "run", "x.png"])
+    assert a.save_opt_record and a.save_reconstruction
+    from sga_b200.cli import parse_args_mbt2018
+    m = parse_args_mbt2018(["mbt2018.py", "--num_filters", "192", "compress", "run", "in.png", "out.tfci"])
+    assert m.command == "compress" and m.output_file == "out.tfci" and m.results_dir == "./results"
+    m = parse_args_mbt2018(["mbt2018.py", "--num_filters", "192", "decompress", "run", "in.tfci"])
+    assert m.command == "decompress" and m.output_file is None
+    from sga_b200 import configs
+    assert configs.get_eval_batch_size(768 * 512) == 25 and configs.get_eval_batch_size(1200 * 1200) == 7   # configs.py:8-9
+    assert configs.save_opt_record is False and configs.write_tfci_for_eval is False
     b = parse_args(["bb_sga.py", "--num_filters", "192", "compress", "mbt2018_bb-num_filters=192-lmbda=0.01", "in.npy"], bb=True)
     assert b.sga_its == 2000 and b.rate_its == 2000 and b.lmbda == -1          # bb_sga.py:186-192
 
