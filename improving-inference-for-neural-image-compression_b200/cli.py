@@ -45,7 +45,8 @@ def parse_args(argv, bb=False):
                    help="(new) arithmetic of the (de)conv stacks inside the loop; init and final eval are always f32.")
     c.add_argument("runname", help="Model name identifier, like 'mbt2018-num_filters=192-lmbda=0.01'")
     c.add_argument("input_file", help="Input filename (image, or .npy uint8 [N,H,W,3]).")
-    c.add_argument("output_file", nargs="?", help="Output filename (optional, unused by sga.py).")
+    c.add_argument("output_file", nargs="?", help="Output filename (optional; the reference never writes it -- here: the "
+                                                  "range-coded bitstream of round(y), round(z), single-process runs).")
     args = parser.parse_args(argv[1:])
     if args.command is None:
         parser.print_usage()
@@ -156,6 +157,13 @@ def compress(args, out=print):
         if save_reconstruction:                               # sga.py:280-291 (single-image inputs only)
             assert num_images == 1
             j["recon_u8"] = torch.round(torch.clamp(recon[0], 0, 1) * 255).to(torch.uint8).cpu().numpy()   # utils.write_png
+        if args.output_file and ws == 1:
+            # (new) the bitstream of what SGA transmits, round(y) and round(z) (sga.py:240-241), with the range coder of
+            # csrc/codec.cu -- the reference accepts an output_file argument but never writes it (sga.py only estimates)
+            from . import codec as Cd
+            cd = Cd.LatentCodec(j["eng"])
+            j["streams"], _, _ = cd.compress(j["st"]["y"], j["st"]["z"], Cd.MODE_SGA)
+            cd.close()
         j["eng"].close()
     rows = np.concatenate(rows, axis=0) if rows else np.zeros((0, 7), dtype=np.float32)
     full = D.gather_rows(rows, num_images, rank, ws, device="cuda" if torch.cuda.is_available() else "cpu")
@@ -172,6 +180,17 @@ def compress(args, out=print):
     save_file = "rd-%s-input=%s.npz" % (args.runname, input_file)
     if SCRIPT_NAME != trained_script_name:                    # sga.py:263-268
         save_file = "rd-%s-lmbda=%g+%s-input=%s.npz" % (SCRIPT_NAME, args.lmbda, args.runname, input_file)
+    if args.output_file and ws == 1:
+        from . import codec as Cd
+        streams = [st_ for j in jobs for st_ in j["streams"]]
+        blob = Cd.pack(streams, Cd.MODE_SGA, args.num_filters, H, Wd)
+        with open(args.output_file, "wb") as f:
+            f.write(blob)
+        results["actual_bpp"] = np.asarray([(len(zs) + len(ys)) * 8.0 / (H * Wd) for zs, ys in streams])
+        say("Wrote %s (%d bytes); Avg actual_bpp: %.4f (estimated %.4f)" % (args.output_file, len(blob), results["actual_bpp"].mean(),
+                                                                        results["est_bpp"].mean()))
+    elif args.output_file:
+        say("output_file is only written by single-process runs")
     np.savez(os.path.join(args.results_dir, save_file), **results)
     if save_opt_record:                                       # sga.py:271-278 (the record of the last batch, as in the reference)
         opt_file = "opt-%s-input=%s.npz" % (args.runname, input_file)
@@ -305,6 +324,8 @@ def compress_mbt2018(args, out=print):
     from . import weights as Wm
     from .engine import EVAL_FIELDS, SgaEngine
     from .msssim import msssim_per_image
+    if D.world()[0] != 0:                      # a one-shot forward pass: single process (extra torchrun ranks do nothing)
+        return None
     X = load_input(args.input_file)
     num_images, H, Wd = int(X.shape[0]), int(X.shape[1]), int(X.shape[2])
     num_pixels = H * Wd
@@ -347,8 +368,11 @@ def decompress_mbt2018(args, out=print):
     """mbt2018.py:248-295: strings -> z_hat -> (mu, sigma) -> y_hat -> x_hat, written as PNG (one image) or .npy."""
     import torch
     from . import codec as Cd
+    from . import dist as D
     from . import weights as Wm
     from .engine import SgaEngine
+    if D.world()[0] != 0:
+        return None
     with open(args.input_file, "rb") as f:
         data = f.read()
     streams, mode, C, H, Wd = Cd.unpack(data)

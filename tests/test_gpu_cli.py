@@ -160,3 +160,19 @@ def test_compress_cli_two_ranks_many_batches_match_one(tmp_path):
     assert len(lines[0]) == 3 and len(lines[1]) == 3, lines
     nums = [np.array([[float(v) for v in re.findall(r"=(-?[0-9.]+)", l)] for l in ls]) for ls in lines]
     assert np.allclose(nums[0], nums[1], rtol=2e-4, atol=2e-4), lines
+
+
+def test_compress_cli_writes_the_bitstream_of_the_sga_result(tmp_path):
+    """With an output file, sga.py writes the range-coded round(y), round(z) (sga.py:240-241) and reports the actual rate."""
+    from sga_b200 import codec as Cd
+    rn, inp = _setup(tmp_path, n=2, h=64, w=96)
+    out_file = tmp_path / "out.sgac"
+    cmd = [sys.executable, os.path.join(ROOT, "sga.py"), "--num_filters", "64", "--checkpoint_dir", str(tmp_path / "ckpt"),
+           "compress", "--sga_its", "6", "--results_dir", str(tmp_path / "res"), rn, str(inp), str(out_file)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Avg actual_bpp:" in r.stdout
+    streams, mode, C, H, W = Cd.unpack(out_file.read_bytes())
+    assert (mode, C, H, W) == (Cd.MODE_SGA, 64, 64, 96) and len(streams) == 2
+    d = np.load(tmp_path / "res" / ("rd-sga-lmbda=0.01+%s-input=imgs.npy.npz" % rn))
+    assert d["actual_bpp"].shape == (2,) and (d["actual_bpp"] > 0).all()
