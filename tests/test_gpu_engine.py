@@ -372,3 +372,31 @@ def test_grad_bf16_unfused_fallback(C, n, h, w, monkeypatch):
     assert abs(s["train_mse"] - float(ref["train_mse"])) <= 1.5e-3 * abs(float(ref["train_mse"]))
     assert rms_rel_err(gy, ref["grad_y"]) < 1e-2 and rms_rel_err(gz, ref["grad_z"]) < 9e-2
     eng.close()
+
+
+def test_baseline_config1_matches_the_cpu_oracle():
+    """BASELINE.json configs[0]: one 256x256 synthetic uint8 image, num_filters = 192, lambda = 0.01, 10 SGA steps on the CPU --
+    the oracle's loop (init sga.py:207, 10 x {graph + Adam} :210-215, hard-rounded evaluation :240-247) against the device,
+    same Philox stream: the fp32 path to the north-star tolerance (1e-3 bpp, 0.01 dB; measured ~1e-6), the bf16 tcgen05 loop
+    too (10 iterations are far below the horizon at which the annealing turns chaotic)."""
+    import sga_b200
+    from sga_b200.schedule import annealed_temperature
+    C, n, h, w, its, lmbda = 192, 1, 256, 256, 10, 0.01
+    Wd = sga_b200.weights.make_synthetic(C, 0)
+    img = sga_b200.synth.synthetic_images(n, h, w, 0)
+    x = torch.from_numpy(img.astype(np.float32) / 255.0)
+    y_o, z_o, ev_o = O.sga_run(x, Wd, lmbda, its, seed=0)
+    temps = [annealed_temperature(it, r=1e-3, ub=0.5, scheme="exp0", t0=700) for it in range(its)]
+    for operand, tol_bpp, tol_db, tol_y in (("f32", 1e-4, 1e-3, 1e-3), ("bf16", 1e-3, 0.01, None)):
+        eng = _engine(Wd, n, h, w, C, lmbda, operand, seed=0)
+        y, z = eng.encode_init(x.cuda())
+        st = eng.new_state(y, z)
+        eng.loop(x.cuda(), st, temps, 0)
+        ev = eng.eval_hard(x.cuda(), st["y"], st["z"])
+        print("CONFIG1 %s est_bpp %.6f (oracle %.6f) psnr %.5f (oracle %.5f)" % (operand, ev["est_bpp"][0], float(ev_o["est_bpp"][0]),
+                                                                                ev["psnr"][0], float(ev_o["psnr"][0])))
+        assert abs(ev["est_bpp"][0] - float(ev_o["est_bpp"][0])) <= tol_bpp
+        assert abs(ev["psnr"][0] - float(ev_o["psnr"][0])) <= tol_db
+        if tol_y is not None:
+            assert (st["y"].cpu() - y_o).abs().max().item() <= tol_y
+        eng.close()
