@@ -400,3 +400,28 @@ def test_baseline_config1_matches_the_cpu_oracle():
         if tol_y is not None:
             assert (st["y"].cpu() - y_o).abs().max().item() <= tol_y
         eng.close()
+
+
+def test_loop_graph_replay_across_table_uploads(monkeypatch):
+    """SGA_GRAPH=1 over 1100 iterations in one call: the step-parameter table holds 1024 entries, so the loop uploads it
+    twice and resets the device counter in between; the result must equal the eager loop's (same kernels, same arguments:
+    the latents agree to rounding noise even after 1100 steps of a chaotic optimisation only if every iteration read the
+    right temperature / noise step / lr_t)."""
+    from sga_b200.schedule import annealed_temperature
+    C, n, h, w, its = 64, 1, 64, 64, 1100
+    W, Wt, x, _, _ = make_case(C, n, h, w, seed=13)
+    xd = x.cuda()
+    temps = [annealed_temperature(it, r=2e-3, ub=0.5, scheme="exp0", t0=300) for it in range(its)]
+    out = {}
+    for graph in ("0", "1"):
+        monkeypatch.setenv("SGA_GRAPH", graph)
+        eng = _engine(W, n, h, w, C, 0.01, "bf16", seed=4)
+        y, z = eng.encode_init(xd)
+        st = eng.new_state(y, z)
+        eng.loop(xd, st, temps, 0)
+        torch.cuda.synchronize()
+        out[graph] = (st["y"].clone(), st["z"].clone(), eng.stats.cpu().numpy().copy())
+        eng.close()
+    assert torch.isfinite(out["1"][0]).all()
+    assert torch.equal(out["0"][0], out["1"][0]) and torch.equal(out["0"][1], out["1"][1])
+    assert np.allclose(out["0"][2], out["1"][2], rtol=1e-5, atol=1e-6)
