@@ -30,7 +30,11 @@ using namespace tc;
 constexpr int kL3Groups = 3;
 constexpr int kL3GroupWarps = 4;
 constexpr int kL3GroupThreads = 32 * kL3GroupWarps;
-constexpr int kL3Threads = 64 + kL3Groups * kL3GroupThreads;
+// REALLOC: the two issue warps become a whole warpgroup (two of its warps idle) that drops to 56 registers, and the three
+// epilogue warpgroups take the freed ones (setmaxnreg: 152 instead of the 128 that 14-16 warps start with) -- at 128 the
+// epilogue spilled the prefetched image values and loop invariants inside its per-tile chain.
+constexpr int l3f_issue_threads(bool realloc) { return realloc ? 128 : 64; }
+constexpr int l3f_threads(bool realloc) { return l3f_issue_threads(realloc) + kL3Groups * kL3GroupThreads; }
 constexpr int kL3MaxStages = 8;       // the ring takes what shared memory is left (7 stages at C = 192, 6 at C = 256)
 constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
@@ -52,8 +56,10 @@ struct alignas(64) L3FwdParams {
   int stages;         // A-tile ring depth
 };
 
-__global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant__ L3FwdParams P) {
+template <bool REALLOC>
+__global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid_constant__ L3FwdParams P) {
   pdl_launch_dependents();
+  constexpr int kIssueThreads = l3f_issue_threads(REALLOC), kIssueWarps = kIssueThreads / 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -91,6 +97,8 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
   // Issue loops are warp-uniform with one elected lane (as in conv_tc.cu): a single-lane loop makes the compiler wrap every
   // UTMALDG / UTCHMMA in an election loop with R2UR moves -- hundreds of cycles of dependent-issue latency per K chunk,
   // which at 3 K chunks per tile is what this kernel's fixed ~2300 cycles per tile were made of.
+  if (warp < kIssueWarps) {
+  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(bar_b, P.kchunks * b_chunk);
@@ -144,13 +152,15 @@ __global__ void __launch_bounds__(kL3Threads, 1) k_l3_fwd(const __grid_constant_
       }
       if (elect_one()) umma_commit(bar_tfull + 8 * buf);
     }
+  }
   } else {
-    // Two epilogue groups of 4 warps: group g drains the tiles with (it & 1) == g, i.e. TMEM / P buffer g.  The x
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // Epilogue groups of 4 warps: group g drains the tiles with it % kL3Groups == g, i.e. TMEM / P buffer g.  The x
     // values of a thread's output pixels are fetched one tile ahead (the col2im loop is otherwise bound by that latency).
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-    const int grp = (warp - 2) / kL3GroupWarps;
+    const int grp = (warp - kIssueWarps) / kL3GroupWarps;
     const int row = q * 32 + lane;
-    const int et = (threadIdx.x - 64) % kL3GroupThreads;    // thread index inside the group
+    const int et = (threadIdx.x - kIssueThreads) % kL3GroupThreads;    // thread index inside the group
     const int Ho = 2 * P.Hin, Wo = 2 * P.Win;
     constexpr int kPix = 2 * kL3IntH * 2 * kL3IntW;         // 336 output pixels per tile
     constexpr int kPer = (kPix + kL3GroupThreads - 1) / kL3GroupThreads;   // 3 per thread
@@ -521,10 +531,15 @@ __device__ __forceinline__ void l3_build_groups(const uint2* __restrict__ reg, i
 // 32 registers per 32-column chunk on top of the working set: with 256 columns that spilled at every thread count tried
 // (576 threads / 96 registers: 2.0 ms, 68 % of the stall samples on local-memory loads).
 constexpr int l3_groups(int nf) { return nf / 64; }
-template <int NF>
+// PAIR (NF <= 192): the lanes of a pair (two horizontally adjacent pixels) exchange half of their output so that every
+// store instruction writes 64 contiguous bytes per pixel.  A warp store of one 32-byte sector per lane touches 32 lines and
+// drains at about one line per clock: with all 12 worker warps storing at the end of a tile that was ~1500 clocks per tile
+// of write-after-read stalls on the store operands (17 % of the stall samples); 16 lines per instruction: 0.67 -> 0.62 ms.
+template <int NF, bool PAIR = (NF != 256)>
 __global__ void __launch_bounds__(64 + 128 * l3_groups(NF), 1) k_l3_dgrad_igdn(const __grid_constant__ L3DgradFusedParams P) {
   pdl_launch_dependents();
   constexpr bool kDirect = (NF == 256);
+  static_assert(!(kDirect && PAIR), "the direct mode stores 16-column units");
   constexpr int G = l3_groups(NF);           // worker groups (column split)
   constexpr int NH = NF / (32 * G);          // 32-column chunks per worker warp: chunk c = grp + h * G, h < NH
   constexpr int kWorkers = 128 * G;
@@ -904,7 +919,30 @@ __global__ void __launch_bounds__(64 + 128 * l3_groups(NF), 1) k_l3_dgrad_igdn(c
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_nempty);
         }
-        if (valid) {
+        if constexpr (PAIR) {
+          // lanes 2k, 2k+1 = pixels (i, j), (i, j+1) with j even: afterwards the even lane holds the first 32 bytes of both
+          // pixels' 64-byte pieces and the odd lane the second 32 bytes; one store instruction per pixel of the pair
+          uint32_t o[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t kw = keep[h][e];
+            const uint32_t xw = xk[h][e];
+            o[e] = pack_bf16(l3_bf16_lo(kw) + l3_bf16_lo(xw) * __uint_as_float(m[2 * e]),
+                             l3_bf16_hi(kw) + l3_bf16_hi(xw) * __uint_as_float(m[2 * e + 1]));
+          }
+          const bool odd = (lane & 1) != 0;
+          uint32_t oa[8], ob[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? o[e] : o[8 + e], 1);
+            oa[e] = odd ? got : o[e];        // pixel j:   own first half   | the even lane's second half
+            ob[e] = odd ? o[8 + e] : got;    // pixel j+1: the odd lane's first half | own second half
+          }
+          const long long offe = off0 - (odd ? NF : 0) + c * 32 + (odd ? 16 : 0);
+          const int je = j & ~1;
+          if (i < P.Hin && je < P.Win) st_global_v8(P.out + offe, oa);
+          if (i < P.Hin && je + 1 < P.Win) st_global_v8(P.out + offe + NF, ob);
+        } else if (valid) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             uint32_t o[8];
@@ -1059,11 +1097,13 @@ int l3_tc_create(const __nv_bfloat16* act, const __nv_bfloat16* w_scatter, const
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SGA_CUDA(cudaFuncSetAttribute(k_l3_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA(cudaFuncSetAttribute(k_l3_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SGA_CUDA((cudaFuncSetAttribute(k_l3_dgrad_igdn<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
     SGA_CUDA(cudaFuncSetAttribute(k_l3_dgrad_igdn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -1079,7 +1119,9 @@ int l3_tc_forward(const L3Tc* c, const float* bias_dev_host3, const float* x, fl
   L3FwdParams F = c->F;
   F.bias[0] = bias_dev_host3[0]; F.bias[1] = bias_dev_host3[1]; F.bias[2] = bias_dev_host3[2];
   F.x = x; F.grad_scale = grad_scale; F.xt_out = xt_out; F.gx = gx; F.sse = sse; F.sse_r = sse_r;
-  SGA_TRY(launch_pdl(k_l3_fwd, c->f_grid, kL3Threads, c->f_smem, st, F));
+  static const bool realloc = [] { const char* e = getenv("SGA_L3F_REALLOC"); return !(e && atoi(e) == 0); }();   // A/B switch
+  if (realloc) SGA_TRY(launch_pdl(k_l3_fwd<true>, c->f_grid, l3f_threads(true), c->f_smem, st, F));
+  else SGA_TRY(launch_pdl(k_l3_fwd<false>, c->f_grid, l3f_threads(false), c->f_smem, st, F));
   return SGA_OK;
 }
 
@@ -1102,7 +1144,11 @@ int l3_tc_dgrad_igdn(const L3Tc* c, const __nv_bfloat16* gx, __nv_bfloat16* out,
   D.gx = gx; D.out = out;
   const int threads = 64 + 128 * l3_groups(C);
   if (C == 256) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<256>, c->d_grid, threads, c->df_smem, st, D));
-  else if (C == 192) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
+  else if (C == 192) {
+    static const bool pair = [] { const char* e = getenv("SGA_L3D_PAIR"); return !(e && atoi(e) == 0); }();   // A/B switch
+    if (pair) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<192>, c->d_grid, threads, c->df_smem, st, D));
+    else SGA_TRY((launch_pdl(k_l3_dgrad_igdn<192, false>, c->d_grid, threads, c->df_smem, st, D)));
+  }
   else if (C == 128) SGA_TRY(launch_pdl(k_l3_dgrad_igdn<128>, c->d_grid, threads, c->df_smem, st, D));
   else SGA_TRY(launch_pdl(k_l3_dgrad_igdn<64>, c->d_grid, threads, c->df_smem, st, D));
   return SGA_OK;
