@@ -40,6 +40,27 @@ constexpr int kL3NPad = 80;
 constexpr int kPsStride = 81;
 constexpr int kL3IntH = 6, kL3IntW = 14;   // interior of the 8x16 tile
 
+// (img, tile row, tile column) of tile = first + k * stride for k = 0, 1, ...: advanced with carries instead of the two
+// integer divisions per use (the worker warps of the fused dgrad needed three such pairs per tile, ~10 % of their
+// instruction stream)
+struct L3TileIter {
+  int img, th, tw;
+  int dimg, dth, dtw, tiles_h, tiles_w;
+  __device__ __forceinline__ void init(int first, int stride, int th_n, int tw_n) {
+    tiles_h = th_n; tiles_w = tw_n;
+    const int per_img = th_n * tw_n;
+    img = first / per_img; th = (first % per_img) / tw_n; tw = first % tw_n;
+    dimg = stride / per_img; dth = (stride % per_img) / tw_n; dtw = stride % tw_n;
+  }
+  __device__ __forceinline__ void advance() {
+    tw += dtw;
+    if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+    th += dth;
+    if (th >= tiles_h) { th -= tiles_h; ++img; }
+    img += dimg;
+  }
+};
+
 struct alignas(64) L3FwdParams {
   CUtensorMap amap;   // activation [N,Hin,Win,C] bf16
   CUtensorMap bmap;   // scatter weights [80][C] bf16
@@ -175,9 +196,9 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
       acc_s = 0.0f; acc_r = 0.0f;
     };
     float xn[kPer][3];
-    auto fetch_x = [&](int tile) {
-      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
-      const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
+    auto fetch_x = [&](const L3TileIter& t) {
+      const int img = t.img;
+      const int hi0 = t.th * kL3IntH, wi0 = t.tw * kL3IntW;
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
         const int p = et + k * kL3GroupThreads;
@@ -189,11 +210,14 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
       }
     };
     const int first = blockIdx.x + grp * gridDim.x;
-    if (first < P.total_tiles) fetch_x(first);
+    L3TileIter ti, tn;                   // this group's current tile / the tile whose x values are fetched (one ahead)
+    ti.init(first, kL3Groups * static_cast<int>(gridDim.x), P.tiles_h, P.tiles_w);
+    tn = ti;
+    if (first < P.total_tiles) fetch_x(tn);
     int it = grp;
-    for (int tile = first; tile < P.total_tiles; tile += kL3Groups * gridDim.x, it += kL3Groups) {
-      const int img = tile / tiles_per_img, tt = tile % tiles_per_img;
-      const int hi0 = (tt / P.tiles_w) * kL3IntH, wi0 = (tt % P.tiles_w) * kL3IntW;
+    for (int tile = first; tile < P.total_tiles; tile += kL3Groups * gridDim.x, it += kL3Groups, ti.advance()) {
+      const int img = ti.img;
+      const int hi0 = ti.th * kL3IntH, wi0 = ti.tw * kL3IntW;
       const int buf = grp;
       if (img != acc_img) { flush(); acc_img = img; }   // warp-uniform
       float xc[kPer][3];
@@ -201,7 +225,8 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
       for (int k = 0; k < kPer; ++k)
 #pragma unroll
         for (int c = 0; c < 3; ++c) xc[k][c] = xn[k][c];
-      if (tile + kL3Groups * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tile + kL3Groups * gridDim.x);
+      tn.advance();
+      if (tile + kL3Groups * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tn);
       float* Pb = Ps + buf * 128 * kPsStride;
       mbar_wait(bar_tfull + 8 * buf, (it / kL3Groups) & 1);
       tcgen05_fence_after();
@@ -459,27 +484,6 @@ struct alignas(64) L3DgradFusedParams {
   int N, Hin, Win, C;
   int tiles_h, tiles_w, total_tiles;
   int prefetch;                // L2 prefetch distance of the x / s tiles, in tiles (env SGA_L3_PREFETCH, default 0 = off)
-};
-
-// (img, tile row, tile column) of tile = first + k * stride for k = 0, 1, ...: advanced with carries instead of the two
-// integer divisions per use (the worker warps of the fused dgrad needed three such pairs per tile, ~10 % of their
-// instruction stream)
-struct L3TileIter {
-  int img, th, tw;
-  int dimg, dth, dtw, tiles_h, tiles_w;
-  __device__ __forceinline__ void init(int first, int stride, int th_n, int tw_n) {
-    tiles_h = th_n; tiles_w = tw_n;
-    const int per_img = th_n * tw_n;
-    img = first / per_img; th = (first % per_img) / tw_n; tw = first % tw_n;
-    dimg = stride / per_img; dth = (stride % per_img) / tw_n; dtw = stride % tw_n;
-  }
-  __device__ __forceinline__ void advance() {
-    tw += dtw;
-    if (tw >= tiles_w) { tw -= tiles_w; ++th; }
-    th += dth;
-    if (th >= tiles_h) { th -= tiles_h; ++img; }
-    img += dimg;
-  }
 };
 
 __device__ __forceinline__ float l3_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
