@@ -195,18 +195,38 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
       }
       acc_s = 0.0f; acc_r = 0.0f;
     };
+    // Everything about a thread's (up to) three output pixels that does not depend on the tile is computed once: position
+    // inside the tile, offsets into the image / gradient tensors relative to the tile origin, and the address of tap
+    // (o_y, o_x) = (0, 0), kernel index (py + 2, px + 2) inside the partial-sum buffer -- every other tap is a compile-time
+    // offset from it.  (Recomputed per tile this address arithmetic was a third of the epilogue's instructions.)
+    int ry[kPer], rx[kPer], xoff[kPer], ooff[kPer];
+    float my[kPer], mx[kPer], mxy[kPer];     // 1 where the o = -1 taps exist (even output row / column), else 0
+    const float* pq[kPer];
+    float* const Pb = Ps + grp * 128 * kPsStride;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int p = et + k * kL3GroupThreads;
+      ry[k] = p / (2 * kL3IntW); rx[k] = p % (2 * kL3IntW);
+      if (p >= kPix) { ry[k] = 1 << 20; rx[k] = 0; }          // never inside the image: fails every bound below
+      const int py = ry[k] & 1, px = rx[k] & 1;
+      my[k] = (py == 0) ? 1.0f : 0.0f; mx[k] = (px == 0) ? 1.0f : 0.0f; mxy[k] = my[k] * mx[k];
+      const int tr = ((ry[k] >> 1) + 1) & 7, tcx = (rx[k] >> 1) + 1;   // tile coordinates of the co-located input pixel
+      pq[k] = Pb + (tr * 16 + tcx) * kPsStride + ((py + 2) * 5 + (px + 2)) * 3;
+      const int ryc = (p >= kPix) ? 0 : ry[k];
+      xoff[k] = (ryc * P.W + rx[k]) * 3;
+      ooff[k] = ryc * Wo + rx[k];
+    }
+    Pb[row * kPsStride + kL3NPad] = 0.0f;    // the pad column is read (times 0) by the non-existent taps
     float xn[kPer][3];
     auto fetch_x = [&](const L3TileIter& t) {
-      const int img = t.img;
-      const int hi0 = t.th * kL3IntH, wi0 = t.tw * kL3IntW;
+      const int oy0 = 2 * t.th * kL3IntH, ox0 = 2 * t.tw * kL3IntW;
+      const float* xb = P.x + ((static_cast<long long>(t.img) * P.H + oy0) * P.W + ox0) * 3;
+      const int ly = P.H - oy0, lx = P.W - ox0;
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
-        const int p = et + k * kL3GroupThreads;
-        const int oy = 2 * hi0 + p / (2 * kL3IntW), ox = 2 * wi0 + p % (2 * kL3IntW);
-        const bool in = (p < kPix) && (oy < P.H) && (ox < P.W);
-        const float* xp = P.x + ((static_cast<long long>(img) * P.H + oy) * P.W + ox) * 3;
+        const bool in = (ry[k] < ly) && (rx[k] < lx);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) xn[k][c] = in ? __ldg(xp + c) : 0.0f;
+        for (int c = 0; c < 3; ++c) xn[k][c] = in ? __ldg(xb + xoff[k] + c) : 0.0f;
       }
     };
     const int first = blockIdx.x + grp * gridDim.x;
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
     int it = grp;
     for (int tile = first; tile < P.total_tiles; tile += kL3Groups * gridDim.x, it += kL3Groups, ti.advance()) {
       const int img = ti.img;
-      const int hi0 = ti.th * kL3IntH, wi0 = ti.tw * kL3IntW;
+      const int oy0 = 2 * ti.th * kL3IntH, ox0 = 2 * ti.tw * kL3IntW;
       const int buf = grp;
       if (img != acc_img) { flush(); acc_img = img; }   // warp-uniform
       float xc[kPer][3];
@@ -227,7 +247,6 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
         for (int c = 0; c < 3; ++c) xc[k][c] = xn[k][c];
       tn.advance();
       if (tile + kL3Groups * static_cast<int>(gridDim.x) < P.total_tiles) fetch_x(tn);
-      float* Pb = Ps + buf * 128 * kPsStride;
       mbar_wait(bar_tfull + 8 * buf, (it / kL3Groups) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
@@ -248,33 +267,36 @@ __global__ void __launch_bounds__(l3f_threads(REALLOC), 1) k_l3_fwd(const __grid
       named_bar_sync(1 + grp, kL3GroupThreads);   // all 128 rows of P are in shared memory; TMEM buffer drained
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       // ---- col2im + distortion: 12 x 28 output pixels of this tile's interior
+      const long long opix0 = (static_cast<long long>(img) * Ho + oy0) * Wo + ox0;
+      const int ly = Ho - oy0, lx = Wo - ox0, lyx = P.H - oy0, lxx = P.W - ox0;
+      // branch-free overlap-add of the thread's three pixels side by side (nine independent accumulation chains): a tap
+      // that does not exist for the pixel's parity is multiplied by 0 -- it reads finite values of the same buffer
+      float v[kPer][3];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) { v[k][0] = P.bias[0]; v[k][1] = P.bias[1]; v[k][2] = P.bias[2]; }
+      // out[2i'+py] takes k[a], a = py + 2 - 2o, from input row i'+o (conv_plan.cu): o = -1 only for py = 0
+#pragma unroll
+      for (int oyy = 1; oyy >= -1; --oyy)
+#pragma unroll
+        for (int oxx = 1; oxx >= -1; --oxx)
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) {
+            const float* pp = pq[k] + (oyy * 16 + oxx) * kPsStride - (10 * oyy + 2 * oxx) * 3;
+            if (oyy >= 0 && oxx >= 0) {
+              v[k][0] += pp[0]; v[k][1] += pp[1]; v[k][2] += pp[2];
+            } else {
+              const float m = (oyy < 0 && oxx < 0) ? mxy[k] : (oyy < 0 ? my[k] : mx[k]);
+              v[k][0] = fmaf(m, pp[0], v[k][0]); v[k][1] = fmaf(m, pp[1], v[k][1]); v[k][2] = fmaf(m, pp[2], v[k][2]);
+            }
+          }
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
-        const int p = et + k * kL3GroupThreads;
-        if (p >= kPix) continue;
-        const int ry = p / (2 * kL3IntW), rx = p % (2 * kL3IntW);
-        const int oy = 2 * hi0 + ry, ox = 2 * wi0 + rx;
-        if (oy >= Ho || ox >= Wo) continue;
-        const int py = ry & 1, px = rx & 1;
-        const int tr = (ry >> 1) + 1, tcx = (rx >> 1) + 1;   // tile coordinates of the co-located input pixel
-        float v0 = P.bias[0], v1 = P.bias[1], v2 = P.bias[2];
-        // out[2i'+py] takes k[a], a = py + 2 - 2o, from input row i'+o (conv_plan.cu)
-#pragma unroll
-        for (int oyy = 1; oyy >= -1; --oyy) {
-          const int a = py + 2 - 2 * oyy;
-          if (a < 0 || a > 4) continue;
-#pragma unroll
-          for (int oxx = 1; oxx >= -1; --oxx) {
-            const int b = px + 2 - 2 * oxx;
-            if (b < 0 || b > 4) continue;
-            const float* pp = Pb + ((tr + oyy) * 16 + (tcx + oxx)) * kPsStride + (a * 5 + b) * 3;
-            v0 += pp[0]; v1 += pp[1]; v2 += pp[2];
-          }
-        }
-        const long long opix = (static_cast<long long>(img) * Ho + oy) * Wo + ox;
+        if (ry[k] >= ly || rx[k] >= lx) continue;
+        const float v0 = v[k][0], v1 = v[k][1], v2 = v[k][2];
+        const long long opix = opix0 + ooff[k];
         if (P.xt_out) { P.xt_out[opix * 3] = v0; P.xt_out[opix * 3 + 1] = v1; P.xt_out[opix * 3 + 2] = v2; }
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        if (oy < P.H && ox < P.W) {
+        if (ry[k] < lyx && rx[k] < lxx) {
           const float vv[3] = {v0, v1, v2};
           float gg[3];
 #pragma unroll
