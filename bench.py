@@ -107,8 +107,55 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    # NVML reasons bit mask (nvml.h: nvmlClocksEventReason*)
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def _start_nvml(self, device_index):
+        """In-process NVML polling thread (one sample every ~2 ms): a multi-GPU run's timed region is only tens of
+        milliseconds long, less than it takes an `nvidia-smi -lms` child process to print its first line."""
+        import threading
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        u = str(torch.cuda.get_device_properties(device_index).uuid)
+        u = u if u.startswith("GPU-") else "GPU-" + u
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID(u)
+        self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        self.nvml_sm, self.nvml_mask, self.nvml_stop = [], [0], threading.Event()
+
+        def poll():
+            while not self.nvml_stop.is_set():
+                try:
+                    self.nvml_sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.nvml_mask[0] |= int(get_reasons(h))
+                except Exception:
+                    pass
+                self.nvml_stop.wait(0.002)
+        self.nvml = threading.Thread(target=poll, daemon=True)
+        self.nvml.start()
+
+    def _stop_nvml(self, out):
+        self.nvml_stop.set()
+        self.nvml.join(timeout=2)
+        if self.nvml_sm:
+            out.update(sm_mhz=float(np.median(self.nvml_sm)), sm_max_mhz=self.nvml_max, samples=len(self.nvml_sm))
+        out["reasons"] = sorted(nm for bit, nm in self.REASONS if self.nvml_mask[0] & bit)
+        out["sampler"] = "nvml"
+        return out
+
     def __init__(self, device_index):
         self.proc = None
+        self.nvml = None
+        try:
+            self._start_nvml(device_index)
+            return
+        except Exception:
+            self.nvml = None                  # fall back to an nvidia-smi child process
         self.path = "/tmp/sga_bench_clocks_%d.csv" % os.getpid()
         sel = str(device_index)
         try:
@@ -126,6 +173,8 @@ class ClockSampler:
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.nvml is not None:
+            return self._stop_nvml(out)
         if self.proc is None:
             return out
         self.proc.terminate()
