@@ -22,11 +22,12 @@ using namespace tc;
 // =====================================================================================================
 // forward
 // =====================================================================================================
-// warp 0 TMA, warp 1 MMA, then kL3Groups epilogue groups of kL3GroupWarps warps; group g drains the tiles with
-// it % kL3Groups == g (TMEM accumulator g, col2im buffer g).  The kernel's time is a fixed number of SM cycles (ncu: 448 k
-// cycles whatever the DRAM state; L2 prefetch and ring depth change nothing): a tile's epilogue is one dependent chain
-// (accumulator -> registers -> shared memory -> barrier -> overlap-add -> global) of ~4400 cycles whatever the number of warps
-// that share it (8 warps per group: same time as 4), so throughput comes from the number of tiles in flight.
+// warp 0 TMA, warp 1 MMA (REALLOC: + two idle warps completing the warpgroup), then kL3Groups epilogue groups of
+// kL3GroupWarps warps; group g drains the tiles with it % kL3Groups == g (TMEM accumulator g, col2im buffer g).  A tile's
+// epilogue is one dependent chain (accumulator -> registers -> shared memory -> barrier -> overlap-add -> global) whatever the
+// number of warps that share it (8 warps per group: same time as 4), so throughput comes from the number of tiles in flight;
+// L2 prefetch and ring depth change nothing.  What the kernel is left with per tile is the shared-memory traffic of the
+// scatter / col2im formulation.
 constexpr int kL3Groups = 3;
 constexpr int kL3GroupWarps = 4;
 constexpr int kL3GroupThreads = 32 * kL3GroupWarps;
